@@ -1,0 +1,309 @@
+#!/usr/bin/env python
+"""bench.py — motion frames/sec of the DiffuseStyleGesture sampling hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W            # this framework (libdsg, sm_100a)
+    python bench.py --impl reference --gpus N --steps K ...   # the reference algorithm on the host cores
+
+One "step" = one pass of the hot path over one batch of synthetic input: B clips per GPU, each a 320-frame
+ZEGGS clip = 4 sequential 88-frame segments x 1000 DDPM steps (denoiser + posterior), segment hand-off included
+(BASELINE.json configs[1]; reference main/mydiffusion_zeggs/sample.py:236-296).  Weak scaling: every rank runs
+B clips; clips are independent, so there is no data-path collective — only the final gather of motions.
+
+`value`  : frames/s with conditioning features already resident in HBM, result left on the device.
+`e2e`    : frames/s through the public API (sample.inference_batch) with pinned HOST feature buffers (H2D of
+           each segment's features inside the timed region) and the D2H read of the finished motions.
+`roofline`: dominant kernel class, algorithmic FLOPs / CUDA-event time measured in a separate profiled pass.
+`cpu_baseline`: the oracle port of the reference (torch fp32 CPU, all host threads), bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = "motion frames/sec (1000-step DDPM, 320-frame ZEGGS clips)"
+UNIT = "frames/s"
+N_FRAMES = 320
+# Algorithmic FLOPs per denoiser call and clip, as written in the reference
+FLOP_PER_CLIP_STEP = 1_315_520_512
+FLOP_CLASS = {  # per clip-step, by kernel class (2*M*N*K as written in the reference)
+    "gemm_in": 51_408_896 + 25_952_256, "local_attention": 1_982_464,
+    "gemm_qkv": 8 * 2 * 89 * 256 * 768, "self_attention": 64_888_832, "gemm_outproj": 8 * 2 * 89 * 256 * 256,
+    "gemm_ff1": 8 * 2 * 89 * 256 * 1024, "gemm_ff2": 8 * 2 * 89 * 1024 * 256, "gemm_head_posterior": 51_408_896,
+}
+POSTERIOR_BYTES_PER_CLIP_STEP = 1_204_896       # read x_t, read x0, write x_{t-1} (fp32), noise generated in-kernel
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"], "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace('.', '', 1).isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace('.', '', 1).isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_baseline(sample_steps, batch, threads):
+    """Oracle port of the reference sampler on the host cores: `sample_steps` DDPM steps of one segment at batch
+    `batch`, extrapolated linearly to 4 segments x 1000 steps (every step costs the same: same shapes)."""
+    from diffusestylegesture_b200.config import ZEGGS
+    from diffusestylegesture_b200.synthetic import synthetic_state_dict, synthetic_conditioning
+    from oracle import dsg_oracle as O
+    torch.set_num_threads(threads)
+    g = ZEGGS
+    sd = synthetic_state_dict(g, seed=0)
+    y = synthetic_conditioning(g, batch, segment=0)
+    sched = O.Schedule(1000)
+    with torch.no_grad():
+        O.p_sample_loop(sd, g, sched, y, batch, skip_timesteps=1000 - 3)        # warm-up
+        t0 = time.perf_counter()
+        O.p_sample_loop(sd, g, sched, y, batch, skip_timesteps=1000 - sample_steps)
+        dt = time.perf_counter() - t0
+    per_step = dt / sample_steps
+    clip_seconds = per_step * 1000 * 4
+    return {"value": batch * N_FRAMES / clip_seconds, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{sample_steps} DDPM steps of one 88-frame segment at batch {batch} (oracle/dsg_oracle.py, torch fp32, "
+                      f"{threads} threads; {dt:.1f} s), extrapolated linearly to 4 segments x 1000 steps",
+            "ms_per_denoise_step": per_step * 1e3}
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    vals = []
+    for _ in range(args.warmup):
+        cpu_baseline(max(4, args.ref_sample_steps // 8), args.ref_batch, threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        vals.append(cpu_baseline(args.ref_sample_steps, args.ref_batch, threads))
+    wall = time.perf_counter() - t0
+    v = float(np.mean([c["value"] for c in vals]))
+    cb = dict(vals[-1], value=v)
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": wall / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "ZEGGS 320-frame clips (4 segments x 88 frames), 1000-step DDPM, CPU oracle port of the "
+                                   "reference sampler; each bench step = bounded sample extrapolated", "batch": args.ref_batch},
+            "cpu_baseline": cb,
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="dsg", choices=["dsg", "reference"])
+    ap.add_argument("--batch", type=int, default=0, help="clips per GPU (0 = default for the precision)")
+    ap.add_argument("--precision", default=os.environ.get("DSG_PRECISION", "auto"), choices=["auto", "bf16", "fp32"])
+    ap.add_argument("--ddpm-steps", type=int, default=1000, help="diffusion steps per segment (1000 = the metric's config)")
+    ap.add_argument("--segments", type=int, default=4)
+    ap.add_argument("--ref-sample-steps", type=int, default=240)
+    ap.add_argument("--ref-batch", type=int, default=8)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--profile-steps", type=int, default=40)
+    args = ap.parse_args()
+
+    from diffusestylegesture_b200.distributed import init_from_env, barrier_max_ms, gather_motions
+    if args.impl == "reference":
+        rank = int(os.environ.get("RANK", "0"))
+        run_reference(args, rank, int(os.environ.get("WORLD_SIZE", "1")))
+        return
+
+    rank, world, local = init_from_env()
+    assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: the engine has no CPU fallback (use --impl reference for the CPU arm)")
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    import torch.distributed as dist
+    from diffusestylegesture_b200.config import ZEGGS
+    from diffusestylegesture_b200.mdm import MDM
+    from diffusestylegesture_b200.model_util import create_gaussian_diffusion, load_model_wo_clip
+    from diffusestylegesture_b200.synthetic import synthetic_state_dict, synthetic_conditioning
+    from diffusestylegesture_b200 import sample as S
+
+    g = ZEGGS
+    precision = args.precision
+    sd = synthetic_state_dict(g, seed=0)
+
+    def make_model(prec, mb):
+        m = MDM(njoints=g.njoints, cond_mode='cross_local_attention3_style1', audio_feat='wavlm', n_seed=g.n_seed,
+                precision=prec, max_batch=mb)
+        load_model_wo_clip(m, sd)
+        m.to(dev).eval()
+        m.get_engine(mb)
+        return m
+
+    if precision == "auto":
+        try:
+            make_model("bf16", 1)
+            precision = "bf16"
+        except NotImplementedError:
+            precision = "fp32"
+    B = args.batch or (64 if precision == "bf16" else 8)
+    model = make_model(precision, B)
+    eng = model.get_engine(B)
+    resp = '' if args.ddpm_steps == 1000 else [args.ddpm_steps]
+    diffusion = create_gaussian_diffusion(resp)
+    nseg = args.segments
+    n_frames = nseg * (g.n_poses - g.n_seed)
+    clip0 = rank * B
+    clip_ids = list(range(clip0, clip0 + B))
+    conds = [synthetic_conditioning(g, B, segment=s, clip_offset=clip0) for s in range(nseg)]
+    styles = conds[0]["style"]
+    feats_dev = [c["audio"].to(dev) for c in conds]
+    feats_pin = [c["audio"].pin_memory() for c in conds]
+    styles_pin = styles.pin_memory()
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)     # > 126 MB L2
+
+    def one_step(feats, out_device):
+        return S.inference_batch(model, diffusion, feats, styles_pin if out_device == "cpu" else styles, seed=123456,
+                                 clip_ids=clip_ids, out_device=out_device)
+
+    def timed(feats, out_device, K, W):
+        for _ in range(W):
+            one_step(feats, out_device)
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        total = 0.0
+        l0 = eng.launches
+        for _ in range(K):
+            flush.add_(1.0)                                    # L2 flush between timed iterations (untimed)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            out = one_step(feats, out_device)
+            b.record()
+            torch.cuda.synchronize(dev)
+            total += a.elapsed_time(b)
+        launches = eng.launches - l0
+        if world > 1:
+            dist.barrier()
+        return barrier_max_ms(total, dev), launches, out
+
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    total_ms, launches, out = timed(feats_dev, dev, args.steps, args.warmup)
+    clk = clocks.stop() if rank == 0 else None
+    ms_per_step = total_ms / args.steps
+    frames_all = world * B * n_frames
+    value = frames_all / (ms_per_step * 1e-3)
+
+    e2e = None
+    if not args.no_e2e:
+        e_ms, _, out_h = timed(feats_pin, "cpu", args.steps, 1)
+        gathered = gather_motions(out_h.to(dev), world * B)              # the single collective of the path
+        e2e = {"value": frames_all / (e_ms / args.steps * 1e-3), "unit": UNIT,
+               "h2d_bytes_per_step": int(sum(f.numel() * 4 for f in feats_pin) + styles_pin.numel() * 4),
+               "d2h_bytes_per_step": int(out_h.numel() * 4)}
+        assert rank != 0 or gathered.shape[0] == world * B
+
+    # ---- roofline of the dominant kernel class: separate profiled pass (event pairs around every launch)
+    roofline, kernels = None, None
+    if rank == 0:
+        peaks = load_peaks()
+        psteps = min(args.profile_steps, diffusion.num_timesteps - 1)
+        y = dict(conds[0], audio=feats_dev[0], noise_seed=123456, segment=0, clip_ids=clip_ids)
+        shape = (B, g.njoints, 1, g.n_poses)
+        try:
+            eng.profile(True)
+            diffusion.p_sample_loop(model, shape, clip_denoised=False, model_kwargs={'y': y},
+                                    skip_timesteps=diffusion.num_timesteps - psteps)
+            prof = eng.profile_read()
+            eng.profile(False)
+        except (RuntimeError, NotImplementedError) as ex:
+            prof = {}
+            sys.stderr.write(f"profile pass unavailable: {ex}\n")
+        if prof:
+            tot = sum(ms for _, ms in prof.values())
+            kernels = {k: {"launches": n, "avg_us": ms / n * 1e3, "share": ms / tot} for k, (n, ms) in prof.items()}
+            gemm = {k: v for k, v in prof.items() if k in FLOP_CLASS}
+            dom = max(gemm, key=lambda k: gemm[k][1]) if gemm else None
+            if dom:
+                n, ms = prof[dom]
+                per_launch_flop = FLOP_CLASS[dom] * B / (8 if dom in ("gemm_qkv", "gemm_outproj", "gemm_ff1", "gemm_ff2", "self_attention") else 1)
+                ach = per_launch_flop / (ms / n * 1e-3) / 1e12
+                peak = peaks["bf16_tflops_sustained"]
+                roofline = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                            "traffic": None, "peak_source": peaks["source"] + ", sustained bf16",
+                            "flop_per_launch": per_launch_flop, "avg_launch_us": ms / n * 1e3,
+                            "whole_step": {"achieved": FLOP_PER_CLIP_STEP * B * 1000 * nseg / (ms_per_step * 1e-3) / 1e12 if args.ddpm_steps == 1000 else None,
+                                           "note": "all algorithmic denoiser FLOPs of a bench step / step time"}}
+            if "posterior" in prof:
+                n, ms = prof["posterior"]
+                gbs = POSTERIOR_BYTES_PER_CLIP_STEP * B / (ms / n * 1e-3) / 1e9
+                kernels["posterior"]["hbm_gbs"] = gbs
+                kernels["posterior"]["hbm_frac_of_measured_peak"] = gbs / peaks["hbm_gbs"]
+
+    cb = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cb = cpu_baseline(args.ref_sample_steps, args.ref_batch, os.cpu_count() or 1)
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "bf16" if precision == "bf16" else "f32", "data": "synthetic",
+                "config": {"workload": f"ZEGGS {n_frames}-frame clips = {nseg} sequential segments x 88 frames, "
+                                       f"{diffusion.num_timesteps}-step DDPM, {B} clips per GPU, WavLM-shaped synthetic features "
+                                       "[B,88,1024] per segment, synthetic weights (9.0 M params)",
+                           "clips_per_gpu": B, "global_clips": world * B, "segments": nseg, "ddpm_steps": diffusion.num_timesteps,
+                           "precision": precision, "parallelism": f"clip-dp{world}", "l2": "flushed between timed iterations (256 MB write)"},
+                "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "kernels": kernels, "cpu_baseline": cb,
+                "clocks": clk}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,106 @@
+// Internal engine state shared by dsg_engine.cu (fp32 path, C ABI) and dsg_tc.cu (tcgen05 path).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/dsg.h"
+#include "dsg_common.cuh"
+
+int dsg_fail(int code, const char* fmt, ...);
+
+#define CUDA_TRY(expr)                                                                                  \
+  do {                                                                                                  \
+    cudaError_t err__ = (expr);                                                                         \
+    if (err__ != cudaSuccess) {                                                                         \
+      cudaGetLastError();                                                                               \
+      return dsg_fail(DSG_ERR_CUDA, "%s failed at %s:%d: %s", #expr, __FILE__, __LINE__, cudaGetErrorString(err__)); \
+    }                                                                                                   \
+  } while (0)
+#define TRY(expr) do { int rc__ = (expr); if (rc__) return rc__; } while (0)
+
+// index of each tensor in the `weights` array (== diffusestylegesture_b200/config.py:state_dict_spec order)
+enum {
+  W_AUD_W = 0, W_AUD_B, W_POSE_W, W_POSE_B, W_IN2_W, W_IN2_B, W_T0_W, W_T0_B, W_T2_W, W_T2_B,
+  W_STY_W, W_STY_B, W_TXT_W, W_TXT_B, W_OUT_W, W_OUT_B, W_LAYER0
+};
+enum { L_INPROJ_W = 0, L_INPROJ_B, L_OUTPROJ_W, L_OUTPROJ_B, L_FF1_W, L_FF1_B, L_FF2_W, L_FF2_B, L_N1_W, L_N1_B, L_N2_W, L_N2_B };
+
+struct Stage { void* p = nullptr; size_t cap = 0; };
+
+// kernel classes for the optional per-kernel event timing (dsg_profile)
+enum ProfTag { PT_GEMM_IN = 0, PT_LOCAL_ATTN, PT_GEMM_QKV, PT_SELF_ATTN, PT_GEMM_OUTPROJ, PT_LAYERNORM, PT_GEMM_FF1,
+               PT_GEMM_FF2, PT_GEMM_HEAD, PT_POSTERIOR, PT_OTHER, PT_COUNT };
+struct ProfSpan { int tag; cudaEvent_t a, b; };
+struct dsg_tc_state;
+
+struct dsg_engine {
+  dsg_model_desc d;
+  int S = 0, num_sms = 0;
+  // weights (fp32 slab) and derived tables
+  float* wslab = nullptr;
+  std::vector<float*> w;
+  float *te = nullptr, *TW = nullptr, *Wxp = nullptr, *bxp = nullptr;
+  float2* cs_local = nullptr;
+  // schedule
+  int sampler = 0, nsteps = 0;
+  float4* coef = nullptr;
+  int* tmap = nullptr;
+  std::vector<float> qsample;
+  // conditioning
+  float *emb1 = nullptr, *cvec = nullptr, *enc = nullptr, *cond = nullptr;
+  int cond_batch = 0;
+  // workspace (fp32 path)
+  float *h = nullptr, *xs = nullptr, *qkv = nullptr, *att = nullptr, *ff = nullptr, *tmp = nullptr, *x0 = nullptr;
+  int* tsel = nullptr;
+  long long* clip_ids = nullptr;
+  std::vector<long long> h_clip_ids;
+  int* d_k = nullptr;
+  size_t smem_self = 0, smem_local = 0;
+  // debug taps
+  bool debug = false;
+  float* dbg = nullptr;
+  // host-pointer staging
+  Stage stage[8];
+  int64_t launches = 0;
+  // per-kernel event timing (off by default; never on inside a timed bench region)
+  bool profiling = false;
+  std::vector<ProfSpan> prof_spans;
+  size_t prof_used = 0;
+  double prof_ms[PT_COUNT] = {0};
+  int64_t prof_n[PT_COUNT] = {0};
+  // tensor-core path
+  dsg_tc_state* tc = nullptr;
+  bool graph_valid = false;
+};
+
+// RAII-less span helpers: PROF(e, tag, st, launch-expr)
+int dsg_prof_begin(dsg_engine* e, int tag, cudaStream_t st);
+void dsg_prof_end(dsg_engine* e, cudaStream_t st);
+#define PROF(e, tag, st, expr)                                   \
+  do {                                                           \
+    if ((e)->profiling) dsg_prof_begin((e), (tag), (st));        \
+    int rc_p__ = (expr);                                         \
+    if ((e)->profiling) dsg_prof_end((e), (st));                 \
+    if (rc_p__) return rc_p__;                                   \
+  } while (0)
+
+struct GemmF32Args;
+int launch_gemm_f32(dsg_engine* e, const GemmF32Args& g, bool a_m_contig, bool swap_mn, cudaStream_t st);
+int launch_layernorm(dsg_engine* e, const float* in, float* out, const float* gamma, const float* beta, int rows, int D,
+                     cudaStream_t st);
+int launch_local_attention(dsg_engine* e, int B, const float* h, float* xs, const int* tsel, StepRef step, cudaStream_t st);
+int launch_self_attention(dsg_engine* e, int B, const float* qkv, float* out, cudaStream_t st);
+int launch_posterior(dsg_engine* e, int B, float* x, const float* x0, StepRef step, int index_imm, int draw_imm,
+                     uint64_t seed, int segment, cudaStream_t st);
+int dsg_denoise_step(dsg_engine* e, int B, const float* x, const int* tsel, StepRef step, float* out, cudaStream_t st);
+int dsg_run_steps(dsg_engine* e, int B, float* xd, int n_run, int first_index, uint64_t seed, int segment, cudaStream_t st);
+
+// tensor-core path (dsg_tc.cu)
+int dsg_tc_create(dsg_engine* e);
+void dsg_tc_destroy(dsg_engine* e);
+int dsg_tc_denoise(dsg_engine* e, int B, const float* x, const int* tsel, StepRef step, float* out, cudaStream_t st);
+int dsg_tc_run_steps(dsg_engine* e, int B, float* xd, int n_run, int first_index, uint64_t seed, int segment, cudaStream_t st);

@@ -1,0 +1,245 @@
+"""ZEGGS sampling CLI and segment driver — host mirror of reference main/mydiffusion_zeggs/sample.py
+(argparse :400-407, YAML merge :408-414, create_model_and_diffusion :51-56, inference :210-338, main :341-384).
+
+    python -m diffusestylegesture_b200.sample --config <yml> --gpu 0 --model_path model.pt \
+           --audiowavlm_path 015_Happy_4_x_1_0.wav --max_len 320
+
+Differences from the reference, all additive:
+  * every diffusion step runs inside libdsg (``diffusion.p_sample_loop`` -> one C call per segment);
+  * ``inference_batch`` runs B independent clips in lock-step (the reference is batch 1 only); per clip it
+    reproduces the reference semantics exactly, including the n == 1 "blend" quirk (sample.py:284-288);
+  * conditioning may be given as precomputed WavLM-shaped features (the WavLM-Large forward itself is the
+    next row of the scope table); when a raw wav and a WavLM module are given the
+    reference's ``wav2wavlm`` contract (extract_features + linear interpolation to n_poses) is kept;
+  * new optional YAML keys: ``precision`` (bf16|fp32), ``sampler`` (ddpm|ddim), ``timestep_respacing``.
+"""
+import argparse
+import math
+import os
+import sys
+from datetime import datetime
+from pprint import pprint
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+import yaml
+
+from .mdm import MDM
+from .model_util import create_gaussian_diffusion, load_model_wo_clip
+from .process_zeggs_bvh import pose2bvh
+
+style2onehot = {
+    'Happy': [1, 0, 0, 0, 0, 0],
+    'Sad': [0, 1, 0, 0, 0, 0],
+    'Neutral': [0, 0, 1, 0, 0, 0],
+    'Old': [0, 0, 0, 1, 0, 0],
+    'Angry': [0, 0, 0, 0, 1, 0],
+    'Relaxed': [0, 0, 0, 0, 0, 1],
+}
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+DEFAULT_CONFIG = os.path.join(_HERE, 'configs', 'DiffuseStyleGesture.yml')
+DEFAULT_STATS = os.path.join(_HERE, 'configs', 'zeggs_mean_std.npz')
+
+
+class Config(dict):
+    """Attribute-style dict (stands in for easydict.EasyDict, sample.py:414)."""
+    __getattr__ = dict.__getitem__
+    __setattr__ = dict.__setitem__
+
+
+def create_model_and_diffusion(args):
+    """sample.py:51-56 — same hard-coded ZEGGS geometry; only ``args.audio_feat`` is read by the reference."""
+    model = MDM(modeltype='', njoints=1141, nfeats=1, translation=True, pose_rep='rot6d', glob=True, glob_rot=True,
+                cond_mode='cross_local_attention3_style1', clip_version='ViT-B/32', action_emb='tensor',
+                audio_feat=args.audio_feat, arch='trans_enc', latent_dim=256, n_seed=8,
+                n_poses=getattr(args, 'n_poses', 88) if not isinstance(args, dict) else args.get('n_poses', 88),
+                precision=_get(args, 'precision', 'bf16'), max_batch=_get(args, 'max_batch', 1))
+    diffusion = create_gaussian_diffusion(_get(args, 'timestep_respacing', ''))
+    return model, diffusion
+
+
+def _get(args, key, default):
+    try:
+        return args[key] if isinstance(args, dict) else getattr(args, key)
+    except (KeyError, AttributeError):
+        return default
+
+
+def wav2wavlm(model, wav_input_16khz, device, n_poses=88):
+    """sample.py:44-48 (ZEGGS: no waveform layer-norm).  ``model`` is any WavLM-Large module exposing
+    ``extract_features``; its forward is outside this round's scope (see module docstring)."""
+    rep = model.extract_features(wav_input_16khz.to(device))[0]
+    return F.interpolate(rep.transpose(1, 2), size=n_poses, align_corners=True, mode='linear').transpose(1, 2)
+
+
+def segment_plan(n_frames, n_poses, n_seed):
+    """sample.py:216-222: stride = n_poses - n_seed, floor(n_frames / stride) segments (at least one)."""
+    stride = n_poses - n_seed
+    if n_frames < stride:
+        return 1, n_frames
+    nseg = math.floor(n_frames / stride)
+    return nseg, nseg * stride
+
+
+@torch.no_grad()
+def inference_batch(model, diffusion, features, styles, *, seed=123456, clip_ids=None, smoothing=True,
+                    skip_timesteps=0, sampler='ddpm', device=None, out_device='cpu'):
+    """B clips x S segments through the engine.
+
+    features: sequence (len = segments) of [B, audio_frames, audio_dim] tensors (host or device) — or a callable
+    ``features(segment_index) -> tensor``;  styles: [B, style_in].
+    Returns the normalised motion [B, n_frames - n_seed, J] float32 (sample.py:291-296) on ``out_device``.
+    """
+    g = model.geometry
+    nseg = len(features) if not callable(features) else None
+    if nseg is None:
+        raise ValueError("pass a list of per-segment feature tensors")
+    B = styles.shape[0]
+    eng = model.get_engine(B)
+    dev = eng.device
+    sample_fn = diffusion.p_sample_loop if sampler == 'ddpm' else diffusion.ddim_sample_loop
+    styles = torch.as_tensor(styles, dtype=torch.float32)
+    shape_ = (B, g.njoints, 1, g.n_poses)
+    seed_pose = torch.zeros(B, g.njoints, 1, g.n_seed, device=dev)              # sample.py:244
+    pieces, prev = [], None
+    for i in range(nseg):
+        y = {'style': styles, 'seed': seed_pose, 'audio': features[i],
+             'mask_local': torch.ones(1, g.n_poses, dtype=torch.bool),
+             'noise_seed': seed, 'segment': i, 'clip_ids': clip_ids}
+        sample = sample_fn(model, shape_, clip_denoised=False, model_kwargs={'y': y}, skip_timesteps=skip_timesteps,
+                           init_image=None, progress=False, dump_steps=None, noise=None, const_noise=False)
+        if prev is not None and g.n_seed != 0:                                    # sample.py:266-288
+            tail = prev[..., -g.n_seed:].contiguous()
+            pieces.append(prev[..., :-g.n_seed])
+            eng.stitch_segment(tail, sample, smoothing=smoothing)
+        elif prev is not None:
+            pieces.append(prev)
+        prev = sample
+        seed_pose = sample[..., -g.n_seed:].contiguous()                          # sample.py:249
+    pieces.append(prev[..., :-g.n_seed] if g.n_seed != 0 else prev)               # sample.py:292
+    seq = torch.cat(pieces, dim=-1)[:, :, 0, :].transpose(1, 2)                   # [B, n_frames, J]
+    seq = seq[:, g.n_seed:] if g.n_seed != 0 else seq                             # sample.py:296
+    return seq.contiguous().to(out_device)
+
+
+def denormalise(sampled_seq, stats_path=DEFAULT_STATS):
+    """sample.py:320-326: x * clip(std, 0.01) + mean  (float64 numpy)."""
+    st = np.load(stats_path)
+    std = np.clip(np.array(st['std']).squeeze(), a_min=0.01, a_max=None)
+    return np.multiply(np.asarray(sampled_seq), std) + np.array(st['mean']).squeeze()
+
+
+def inference(args, wavlm_model, audio, sample_fn, model, n_frames=0, smoothing=False, SG_filter=False, minibatch=False,
+              skip_timesteps=0, n_seed=8, style=None, seed=123456, features=None, save_dir='sample_dir',
+              stats_path=DEFAULT_STATS):
+    """Reference signature (sample.py:210) for ONE clip.  ``audio`` is the 16 kHz waveform (numpy); alternatively
+    pass ``features`` = list of per-segment [1, n_poses, 1024] tensors and ``audio=None``.  Writes the BVH."""
+    if not minibatch:
+        raise NotImplementedError("minibatch=False references an undefined variable in the reference (sample.py:302)")
+    torch.manual_seed(seed)
+    g = model.geometry
+    n_poses = _get(args, 'n_poses', g.n_poses)
+    if features is None:
+        if n_frames == 0:
+            n_frames = audio.shape[0] * 20 // 16000
+        nseg, n_frames = segment_plan(n_frames, n_poses, n_seed)
+        audio = audio[:int(n_frames * 16000 / 20)]
+        stride = n_poses - n_seed
+        dev = next(model.parameters()).device
+        chunks = torch.from_numpy(audio).to(torch.float32).reshape(nseg, int(stride * 16000 / 20))
+        pad = int(n_seed * 16000 / 20)
+        features = []
+        for i in range(nseg):                                                     # sample.py:238-251
+            head = torch.zeros(pad) if i == 0 else chunks[i - 1, -pad:]
+            features.append(wav2wavlm(wavlm_model, torch.cat((head, chunks[i]))[None], dev, n_poses))
+    else:
+        nseg = len(features)
+        n_frames = nseg * (n_poses - n_seed)
+    diffusion = getattr(sample_fn, '__self__', None)
+    if diffusion is None:
+        raise ValueError("sample_fn must be diffusion.p_sample_loop or diffusion.ddim_sample_loop")
+    sampler = 'ddim' if sample_fn.__name__ == 'ddim_sample_loop' else 'ddpm'
+    seq = inference_batch(model, diffusion, features, torch.as_tensor([style], dtype=torch.float32), seed=seed,
+                          smoothing=smoothing, skip_timesteps=skip_timesteps, sampler=sampler)
+    out_poses = denormalise(seq[0].numpy(), stats_path)
+    print(out_poses.shape)
+    prefix = str(datetime.now().strftime('%Y%m%d_%H%M%S'))
+    if smoothing: prefix += '_smoothing'
+    if SG_filter: prefix += '_SG'
+    if minibatch: prefix += '_minibatch'
+    prefix += '_%s' % (n_frames)
+    prefix += '_' + str(style)
+    prefix += '_' + str(seed)
+    os.makedirs(save_dir, exist_ok=True)
+    path = os.path.join(save_dir, prefix + '.bvh')
+    pose2bvh(out_poses, path, length=n_frames - n_seed, smoothing=SG_filter)
+    return path, out_poses
+
+
+def load_wav_16k(path):
+    """Mono 16 kHz float32 waveform (stands in for librosa.load(path, sr=16000), sample.py:346)."""
+    import wave
+    with wave.open(path, 'rb') as w:
+        sr, n, ch, width = w.getframerate(), w.getnframes(), w.getnchannels(), w.getsampwidth()
+        raw = w.readframes(n)
+    if width != 2:
+        raise NotImplementedError("only 16-bit PCM wav files are supported")
+    x = np.frombuffer(raw, dtype='<i2').astype(np.float32) / 32768.0
+    if ch > 1:
+        x = x.reshape(-1, ch).mean(axis=1)
+    if sr != 16000:
+        from scipy.signal import resample_poly
+        gdiv = math.gcd(sr, 16000)
+        x = resample_poly(x, 16000 // gdiv, sr // gdiv).astype(np.float32)
+    return x, 16000
+
+
+def main(args, save_dir, model_path, audio_path=None, mfcc_path=None, audiowavlm_path=None, max_len=0, wavlm_model=None,
+         features=None):
+    """sample.py:341-384."""
+    os.makedirs(save_dir, exist_ok=True)
+    print("Creating model and diffusion...")
+    model, diffusion = create_model_and_diffusion(args)
+    print(f"Loading checkpoints from [{model_path}]...")
+    state_dict = torch.load(model_path, map_location='cpu')
+    load_model_wo_clip(model, state_dict)
+    model.to(torch.device('cuda:' + str(args.gpu)))
+    model.eval()
+    sample_fn = diffusion.p_sample_loop if _get(args, 'sampler', 'ddpm') == 'ddpm' else diffusion.ddim_sample_loop
+    style = style2onehot[audiowavlm_path.split('/')[-1].split('_')[1]]
+    print(style)
+    audio = None
+    if features is None:
+        if wavlm_model is None:
+            raise NotImplementedError(
+                "the WavLM-Large forward is not part of this engine yet (SURVEY.md section 8(f).1): pass "
+                "`wavlm_model` (any module with extract_features) or precomputed `features`")
+        audio, _ = load_wav_16k(audiowavlm_path)
+    return inference(args, wavlm_model, audio, sample_fn, model, n_frames=max_len, smoothing=True, SG_filter=True,
+                     minibatch=True, skip_timesteps=0, style=style, seed=123456, features=features, save_dir=save_dir)
+
+
+def parse_cli(argv=None):
+    parser = argparse.ArgumentParser(description='DiffuseStyleGesture')
+    parser.add_argument('--config', default=DEFAULT_CONFIG)
+    parser.add_argument('--gpu', type=str, default='0')
+    parser.add_argument('--no_cuda', type=list, default=['0'])
+    parser.add_argument('--model_path', type=str, default='./model000450000.pt')
+    parser.add_argument('--audiowavlm_path', type=str, default='')
+    parser.add_argument('--max_len', type=int, default=0)
+    args = parser.parse_args(argv)
+    with open(args.config) as f:
+        config = yaml.safe_load(f)
+    for k, v in vars(args).items():
+        config[k] = v
+    return Config(config)
+
+
+if __name__ == '__main__':
+    config = parse_cli()
+    pprint(dict(config))
+    torch.cuda.set_device(int(config.gpu))
+    main(config, 'sample_dir', config.model_path, audio_path=None, mfcc_path=None,
+         audiowavlm_path=config.audiowavlm_path, max_len=config.max_len)

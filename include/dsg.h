@@ -126,6 +126,13 @@ int64_t dsg_kernel_launch_count(const dsg_engine* e);
  * tests: name in {"tok","h_in","h_local","xs0","xs1",...,"xsL"}; returns element count or negative status. */
 int64_t dsg_debug_read(dsg_engine* e, const char* name, int32_t batch, float* dst, int64_t capacity);
 
+/* Optional per-kernel-class CUDA-event timing (bench.py's roofline leg; never enable it inside a timed region:
+ * it brackets every launch with two event records).  enable: 1 = start (resets totals), 0 = stop.
+ * dsg_profile_read returns launches and summed device ms for class `tag` (0 <= tag, name != NULL). */
+int dsg_profile(dsg_engine* e, int32_t enable);
+int dsg_profile_read(dsg_engine* e, int32_t tag, int64_t* count, double* total_ms);
+const char* dsg_profile_tag_name(int32_t tag);
+
 const char* dsg_last_error(void);
 const char* dsg_version(void);
 

@@ -1,0 +1,209 @@
+"""GPU (B200): libdsg through its C ABI against the oracle and the committed reference golden vectors.
+
+Tolerances (normalised motion values are O(1), |x| <= ~2.5):
+  fp32 engine (CUDA cores, validation path):  per-op 1e-4; one denoiser call 2e-4; sampling loops 2e-3.
+  bf16 engine (tcgen05, fp32 accumulate):      see test_gpu_tc.py.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from diffusestylegesture_b200.config import ZEGGS
+from diffusestylegesture_b200.engine import Engine
+from diffusestylegesture_b200.mdm import MDM
+from diffusestylegesture_b200.model_util import create_gaussian_diffusion, load_model_wo_clip
+from diffusestylegesture_b200.synthetic import synthetic_state_dict, synthetic_conditioning
+from diffusestylegesture_b200 import sample as S
+from diffusestylegesture_b200 import process_zeggs_bvh as PB
+from oracle import dsg_oracle as O
+
+pytestmark = pytest.mark.gpu
+SEED = 123456
+G = ZEGGS
+
+
+@pytest.fixture(scope="module")
+def sd():
+    return synthetic_state_dict(G, seed=0)
+
+
+@pytest.fixture(scope="module")
+def eng(sd):
+    e = Engine(G, sd, device=0, max_batch=8, precision="fp32")
+    yield e
+    e.close()
+
+
+def _model(sd, precision="fp32", max_batch=8):
+    m = MDM(njoints=G.njoints, cond_mode='cross_local_attention3_style1', audio_feat='wavlm', n_seed=G.n_seed,
+            precision=precision, max_batch=max_batch)
+    load_model_wo_clip(m, sd)
+    return m.to('cuda:0').eval()
+
+
+def _maxdiff(a, b):
+    return float((torch.as_tensor(a).double().cpu() - torch.as_tensor(b).double().cpu()).abs().max())
+
+
+def test_denoiser_per_op_and_output_vs_reference_golden(gold_dir, sd, eng):
+    gold = np.load(os.path.join(gold_dir, "mdm_forward_zeggs.npz"))
+    y = synthetic_conditioning(G, 2, segment=0)
+    y["seed"] = torch.from_numpy(gold["seed_pose"])
+    x = O.noise_tensor(SEED, [0, 1], 0, 0, (G.njoints, 1, G.n_poses))
+    eng.debug_enable()
+    eng.set_conditioning(y["style"], y["seed"], y["audio"])          # HOST buffers through the C ABI
+    out = eng.denoise(x, gold["t"])                                   # host in, host out
+    assert _maxdiff(eng.debug_read("tok", 2), gold["tap_tok"]) < 1e-4
+    assert _maxdiff(eng.debug_read("h_in", 2), gold["tap_h_in"]) < 1e-4
+    assert _maxdiff(eng.debug_read("xs0", 2), gold["tap_xs0"]) < 1e-4
+    assert _maxdiff(eng.debug_read("xs1", 2), gold["tap_xs1"]) < 1e-4
+    assert _maxdiff(eng.debug_read("xs8", 2), gold["tap_xs8"]) < 2e-4
+    assert _maxdiff(out, gold["out"]) < 2e-4
+    # device buffers in place give the same answer
+    out_d = eng.denoise(x.cuda(), gold["t"])
+    assert out_d.is_cuda and _maxdiff(out_d, out) == 0.0
+
+
+def test_posterior_step_matches_reference_arithmetic(eng):
+    d = create_gaussian_diffusion()
+    coef, qs, tmap = d.engine_tables("ddpm")
+    eng.set_schedule("ddpm", coef, qs, tmap)
+    B, shp = 3, (G.njoints, 1, G.n_poses)
+    x = O.noise_tensor(SEED, [0, 1, 2], 5, 1, shp)
+    x0 = O.noise_tensor(SEED, [0, 1, 2], 5, 2, shp)
+    clip_ids = [7, 11, 2 ** 31 + 5]
+    for index, draw in ((999, 1), (500, 500), (1, 999), (0, 1000)):
+        z = O.noise_tensor(SEED, clip_ids, 3, draw, shp)
+        want = torch.tensor(float(coef[index, 0])) * x0 + torch.tensor(float(coef[index, 1])) * x
+        if index != 0:
+            want = want + torch.tensor(float(coef[index, 2])) * z
+        got = eng.posterior_step(x.clone().cuda(), x0.cuda(), index, SEED, clip_ids=clip_ids, segment=3, draw=draw)
+        assert _maxdiff(got, want) < 3e-6, index          # Box-Muller libm differences only
+    got0 = eng.posterior_step(x.clone().cuda(), x0.cuda(), 0, SEED, clip_ids=clip_ids, segment=3, draw=1000)
+    assert torch.equal(got0.cpu(), x0)                     # c1[0] = 1, c2[0] = 0, no noise at t = 0: exact
+    # DDIM arithmetic
+    dd = create_gaussian_diffusion("ddim100")
+    coef, qs, tmap = dd.engine_tables("ddim")
+    eng.set_schedule("ddim", coef, qs, tmap)
+    for index in (99, 40, 0):
+        c = [torch.tensor(float(v)) for v in coef[index]]
+        eps = (c[0] * x - x0) / c[1]
+        want = x0 * c[2] + c[3] * eps
+        got = eng.posterior_step(x.clone().cuda(), x0.cuda(), index, SEED, clip_ids=clip_ids, segment=0, draw=1)
+        assert _maxdiff(got, want) < 1e-6, index
+
+
+def test_noise_stream_matches_oracle_stream(eng):
+    # x_T drawn by the engine (draw 0) == oracle stream; one 1-step "loop" isolates it: with nsteps=1 the loop
+    # runs index 0 only, whose output is x0_pred — so check the stream through the posterior entry instead.
+    d = create_gaussian_diffusion()
+    coef, qs, tmap = d.engine_tables("ddpm")
+    coef = coef.copy(); coef[5] = [0.0, 0.0, 1.0, 0.0]               # x <- 0*x0 + 0*x + 1*z
+    eng.set_schedule("ddpm", coef, qs, tmap)
+    shp = (G.njoints, 1, G.n_poses)
+    x = torch.zeros((2,) + shp).cuda()
+    got = eng.posterior_step(x, torch.zeros_like(x), 5, 987654321012345, clip_ids=[3, 2 ** 33 + 1], segment=2, draw=77)
+    want = O.noise_tensor(987654321012345, [3, 2 ** 33 + 1], 2, 77, shp)
+    assert _maxdiff(got, want) < 2e-6
+    assert abs(float(got.mean())) < 0.01 and abs(float(got.std()) - 1) < 0.01
+
+
+@pytest.mark.parametrize("tag,resp,sampler,skip", [("ddpm50", [50], "ddpm", 0), ("ddim100", "ddim100", "ddim", 0),
+                                                   ("ddpm1000_skip950", '', "ddpm", 950)])
+def test_sampling_loops_vs_reference_golden(gold_dir, sd, tag, resp, sampler, skip):
+    gold = np.load(os.path.join(gold_dir, "loops_zeggs.npz"))[tag]
+    model = _model(sd)
+    d = create_gaussian_diffusion(resp)
+    y = synthetic_conditioning(G, 2, segment=0)
+    y.update(noise_seed=SEED, segment=0)
+    fn = d.p_sample_loop if sampler == "ddpm" else d.ddim_sample_loop
+    out = fn(model, (2, G.njoints, 1, G.n_poses), clip_denoised=False, model_kwargs={'y': y}, skip_timesteps=skip)
+    assert out.is_cuda and _maxdiff(out, gold) < 2e-3, tag
+
+
+def test_caller_noise_and_init_image(sd):
+    model = _model(sd)
+    d = create_gaussian_diffusion([20])
+    y = synthetic_conditioning(G, 2, segment=0)
+    y.update(noise_seed=SEED, segment=0)
+    shp = (G.njoints, 1, G.n_poses)
+    noise = O.noise_tensor(99, [0, 1], 0, 0, shp)
+    init = 0.3 * O.noise_tensor(98, [0, 1], 0, 0, shp)
+    out = d.p_sample_loop(model, (2,) + shp, noise=noise, clip_denoised=False, model_kwargs={'y': y},
+                          skip_timesteps=5, init_image=init)
+    want, _ = O.p_sample_loop(sd, G, O.Schedule(1000, [20]), y, 2, seed=SEED, segment=0, skip_timesteps=5,
+                              init_image=init, noise=noise)
+    assert _maxdiff(out, want) < 2e-3
+
+
+def test_results_do_not_depend_on_batch_sharding(sd):
+    """Clip ids key the noise stream: running clips {0,1,2,3} together == running {0,1} and {2,3} apart."""
+    model = _model(sd)
+    d = create_gaussian_diffusion([10])
+    y4 = synthetic_conditioning(G, 4, segment=0)
+    shp = (4, G.njoints, 1, G.n_poses)
+    full = d.p_sample_loop(model, shp, clip_denoised=False,
+                           model_kwargs={'y': dict(y4, noise_seed=SEED, segment=0, clip_ids=[0, 1, 2, 3])})
+    for lo in (0, 2):
+        ys = {k: (v[lo:lo + 2] if isinstance(v, torch.Tensor) and v.shape[0] == 4 else v) for k, v in y4.items()}
+        part = d.p_sample_loop(model, (2,) + shp[1:], clip_denoised=False,
+                               model_kwargs={'y': dict(ys, noise_seed=SEED, segment=0, clip_ids=[lo, lo + 1])})
+        assert _maxdiff(part, full[lo:lo + 2]) < 1e-5
+
+
+def test_inference_two_segments_vs_reference_golden(gold_dir, sd, tmp_path):
+    gold = np.load(os.path.join(gold_dir, "inference_zeggs_50.npz"))
+    model = _model(sd)
+    d = create_gaussian_diffusion([50])
+    feats = [synthetic_conditioning(G, 1, segment=s)["audio"] for s in range(2)]
+    path, poses = S.inference(S.Config(n_poses=88, audio_feat="wavlm"), None, None, d.p_sample_loop, model,
+                              smoothing=True, SG_filter=True, minibatch=True, style=list(gold["style"]), seed=SEED,
+                              features=feats, save_dir=str(tmp_path),
+                              stats_path=os.path.join(gold_dir, "zeggs_mean_std.npz"))
+    assert poses.shape == (152, 1141)
+    assert np.abs(poses - gold["poses"]).max() < 0.05            # de-normalised units (cm / unit vectors), fp32 chain
+    pos, eul = PB.pose2bvh_arrays(poses, 152, smoothing=True)
+    assert np.abs(pos - gold["positions"]).max() < 0.05           # cm
+    d_eul = np.abs((eul - gold["rotations"] + 180.0) % 360.0 - 180.0)
+    assert d_eul.max() < 0.5                                       # degrees
+    assert os.path.getsize(path) > 1e6
+
+
+@pytest.mark.slow
+def test_full_clip_1000_steps_vs_reference_golden(gold_dir, sd):
+    """Config 2 of BASELINE.json: one 320-frame clip, 4 segments x 1000 DDPM steps — final BVH joint values."""
+    gold = np.load(os.path.join(gold_dir, "inference_zeggs_1000.npz"))
+    st = np.load(os.path.join(gold_dir, "zeggs_mean_std.npz"))
+    model = _model(sd)
+    d = create_gaussian_diffusion()
+    feats = [synthetic_conditioning(G, 1, segment=s)["audio"] for s in range(4)]
+    seq = S.inference_batch(model, d, feats, torch.tensor([list(gold["style"])], dtype=torch.float32), seed=SEED)
+    poses = O.denormalise(seq[0].numpy(), st["mean"], st["std"])
+    assert np.abs(poses - gold["poses"]).max() < 0.05
+    pos, eul = PB.pose2bvh_arrays(poses, 312, smoothing=True)
+    assert np.abs(pos - gold["positions"]).max() < 0.05
+    d_eul = np.abs((eul - gold["rotations"] + 180.0) % 360.0 - 180.0)
+    assert d_eul.max() < 0.5
+
+
+def test_stitch_quirk_matches_oracle(eng):
+    shp = (G.njoints, 1, G.n_poses)
+    sample = O.noise_tensor(SEED, [0, 1], 1, 3, shp)
+    tail = O.noise_tensor(SEED, [0, 1], 1, 4, (G.njoints, 1, G.n_seed))
+    got = eng.stitch_segment(tail.cuda(), sample.clone().cuda(), smoothing=True).cpu()
+    want = torch.cat([O.stitch_segment(tail[b:b + 1], sample[b:b + 1]) for b in range(2)])
+    assert torch.equal(got, want)
+
+
+def test_bad_arguments_fail_loudly(eng):
+    with pytest.raises(RuntimeError, match="batch"):
+        eng.set_conditioning(torch.zeros(9, 6), torch.zeros(9, G.njoints, 1, G.n_seed), torch.zeros(9, 88, 1024))
+    y = synthetic_conditioning(G, 2, segment=0)
+    eng.set_conditioning(y["style"], y["seed"], y["audio"])
+    with pytest.raises(RuntimeError, match="conditioning"):
+        eng.denoise(torch.zeros(3, G.njoints, 1, G.n_poses), np.zeros(3, dtype=np.int32))
+    with pytest.raises(RuntimeError, match="timestep"):
+        eng.denoise(torch.zeros(2, G.njoints, 1, G.n_poses), np.array([0, 1000], dtype=np.int32))
+    assert eng.launches > 0
