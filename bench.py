@@ -87,6 +87,27 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def host_threads():
+    """CPU threads this process may really use: scheduler affinity capped by the cgroup CPU quota (os.cpu_count()
+    reports the host's cores and oversubscribes a quota-limited container)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = min(n, max(1, int(int(quota) / int(period))))
+    except (OSError, ValueError):
+        pass
+    return max(1, n)
+
+
+def log(msg):
+    sys.stderr.write("[bench %.1fs] %s\n" % (time.perf_counter() - T0, msg))
+    sys.stderr.flush()
+
+
+T0 = time.perf_counter()
+
+
 def cpu_baseline(sample_steps, batch, threads):
     """Oracle port of the reference sampler on the host cores: `sample_steps` DDPM steps of one segment at batch
     `batch`, extrapolated linearly to 4 segments x 1000 steps (every step costs the same: same shapes)."""
@@ -98,6 +119,9 @@ def cpu_baseline(sample_steps, batch, threads):
     sd = synthetic_state_dict(g, seed=0)
     y = synthetic_conditioning(g, batch, segment=0)
     sched = O.Schedule(1000)
+    # the reference draws its noise with torch.randn (gaussian_diffusion.py:542): time THAT, not the numpy Philox
+    # restatement the parity tests use
+    O.noise_tensor = lambda seed, clip_ids, segment, draw, shp: torch.randn((len(clip_ids),) + tuple(shp))
     with torch.no_grad():
         O.p_sample_loop(sd, g, sched, y, batch, skip_timesteps=1000 - 3)        # warm-up
         t0 = time.perf_counter()
@@ -114,7 +138,7 @@ def cpu_baseline(sample_steps, batch, threads):
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
+    threads = host_threads()
     vals = []
     for _ in range(args.warmup):
         cpu_baseline(max(4, args.ref_sample_steps // 8), args.ref_batch, threads)
@@ -232,7 +256,9 @@ def main():
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
+    log(f"timed region: precision {precision}, {B} clips/GPU, {nseg} segments x {diffusion.num_timesteps} steps, W={args.warmup} K={args.steps}")
     total_ms, launches, out = timed(feats_dev, dev, args.steps, args.warmup)
+    log("timed region done: %.1f ms/step" % (total_ms / args.steps))
     clk = clocks.stop() if rank == 0 else None
     ms_per_step = total_ms / args.steps
     frames_all = world * B * n_frames
@@ -241,6 +267,7 @@ def main():
     e2e = None
     if not args.no_e2e:
         e_ms, _, out_h = timed(feats_pin, "cpu", args.steps, 1)
+        log("e2e done: %.1f ms/step" % (e_ms / args.steps))
         gathered = gather_motions(out_h.to(dev), world * B)              # the single collective of the path
         e2e = {"value": frames_all / (e_ms / args.steps * 1e-3), "unit": UNIT,
                "h2d_bytes_per_step": int(sum(f.numel() * 4 for f in feats_pin) + styles_pin.numel() * 4),
@@ -260,6 +287,7 @@ def main():
                                     skip_timesteps=diffusion.num_timesteps - psteps)
             prof = eng.profile_read()
             eng.profile(False)
+            log("profile pass done")
         except (RuntimeError, NotImplementedError) as ex:
             prof = {}
             sys.stderr.write(f"profile pass unavailable: {ex}\n")
@@ -286,7 +314,9 @@ def main():
 
     cb = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cb = cpu_baseline(args.ref_sample_steps, args.ref_batch, os.cpu_count() or 1)
+        log("cpu baseline (oracle port, %d threads)" % host_threads())
+        cb = cpu_baseline(args.ref_sample_steps, args.ref_batch, host_threads())
+        log("cpu baseline done")
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

@@ -27,22 +27,22 @@ DSG_DEVINL float u01_from_u32(uint32_t r) {            // (0,1): top 24 bits, ce
   return (float)(r >> 8) * 5.9604644775390625e-8f + 2.98023223876953125e-8f;
 }
 
-// 4 standard normals for elements 4q..4q+3 of a clip tensor.
+// 4 standard normals for elements 4q..4q+3 of a clip tensor: Box-Muller on the four Philox outputs,
+//   z0 = r cos(2 pi u2), z1 = r sin(2 pi u2), r = sqrt(-2 ln u1)   (same for outputs 2,3).
+// B200-first arithmetic: ln through MUFU.LG2 (__logf) and sin/cos through MUFU.SIN/COS on the angle shifted into
+// (-pi, pi) where the approximation is tight (cos(2 pi u) = -cos(2 pi u - pi)).  ~18 instructions per normal
+// instead of ~40 with libm-accurate logf/sincosf; |error| vs the exact definition (oracle/dsg_oracle.py:
+// philox_normal) is <= ~1e-6 typically, up to ~4e-5 for the rare u1 -> 1 (tiny radius) draws.
+DSG_DEVINL float2 box_muller(uint32_t a, uint32_t b) {
+  const float rad = sqrtf(-2.0f * __logf(u01_from_u32(a)));
+  float s, c;
+  __sincosf(fmaf(6.283185307179586f, u01_from_u32(b), -3.14159265358979f), &s, &c);
+  return make_float2(-rad * c, -rad * s);
+}
 DSG_DEVINL float4 philox_normal4(uint32_t q, uint32_t draw, uint32_t clip, uint32_t segment, uint32_t k0, uint32_t k1) {
   const Philox4 r = philox4x32_10(q, draw, clip, segment, k0, k1);
-  const float two_pi = 6.283185307179586f;
-  float4 o;
-  {
-    const float rad = sqrtf(-2.0f * logf(u01_from_u32(r.x)));
-    float s, c; sincosf(two_pi * u01_from_u32(r.y), &s, &c);
-    o.x = rad * c; o.y = rad * s;
-  }
-  {
-    const float rad = sqrtf(-2.0f * logf(u01_from_u32(r.z)));
-    float s, c; sincosf(two_pi * u01_from_u32(r.w), &s, &c);
-    o.z = rad * c; o.w = rad * s;
-  }
-  return o;
+  const float2 p0 = box_muller(r.x, r.y), p1 = box_muller(r.z, r.w);
+  return make_float4(p0.x, p0.y, p1.x, p1.y);
 }
 
 DSG_DEVINL float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
@@ -59,12 +59,17 @@ DSG_DEVINL float warp_max(float v) {
   return v;
 }
 
-// Per-step scalars every step-dependent kernel needs.  Either immediate (k_imm >= 0) or read from a device
-// counter (CUDA-graph replay: one graph per step, a 1-thread kernel bumps the counter).
+// Per-step scalars every step-dependent kernel needs.  Either immediates, or read from a small device struct
+// (CUDA-graph replay: one captured step is replayed n times; a 1-thread kernel bumps `k` at the end of each).
+struct LoopParams { int k; int first_index; uint32_t key0, key1, segment; int pad[3]; };
 struct StepRef {
-  const int* d_k;     // device loop-iteration counter (nullable)
-  int k_imm;          // loop iteration k (0 = noisiest step) when d_k == nullptr
-  int first_index;    // sampler index of k == 0  (nsteps - skip - 1)
-  DSG_DEVINL int k() const { return d_k ? *d_k : k_imm; }
-  DSG_DEVINL int index() const { return first_index - k(); }
+  const LoopParams* d;   // device loop state (nullable)
+  int k_imm;             // loop iteration k (0 = noisiest step) when d == nullptr
+  int first_imm;         // sampler index of k == 0  (nsteps - skip - 1)
+  uint32_t key0_imm, key1_imm, seg_imm;
+  DSG_DEVINL int k() const { return d ? d->k : k_imm; }
+  DSG_DEVINL int index() const { return (d ? d->first_index : first_imm) - k(); }
+  DSG_DEVINL uint32_t key0() const { return d ? d->key0 : key0_imm; }
+  DSG_DEVINL uint32_t key1() const { return d ? d->key1 : key1_imm; }
+  DSG_DEVINL uint32_t segment() const { return d ? d->segment : seg_imm; }
 };

@@ -254,6 +254,7 @@ extern "C" int dsg_engine_create(const dsg_model_desc* desc, const float* const*
   TRY_CREATE(dalloc(&e->tsel, (size_t)MB));
   TRY_CREATE(dalloc(&e->clip_ids, (size_t)MB));
   TRY_CREATE(dalloc(&e->d_k, (size_t)1));
+  TRY_CREATE(dalloc(&e->d_loop, (size_t)1));
   // opt-in shared memory for the attention kernels
   {
     const int hdg = D / desc->num_heads;
@@ -262,7 +263,8 @@ extern "C" int dsg_engine_create(const dsg_model_desc* desc, const float* const*
     e->smem_local = (size_t)(T * (hdl + 1) + 4 * hdl) * sizeof(float);
     if (e->smem_self > 227 * 1024 || e->smem_local > 227 * 1024) {
       rc = dsg_fail(DSG_ERR_BAD_SHAPE, "sequence too long for the shared-memory attention kernels"); dsg_engine_destroy(e); return rc; }
-    cudaFuncSetAttribute(self_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_self);
+    cudaFuncSetAttribute(self_attention_kernel<float, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_self);
+    cudaFuncSetAttribute(self_attention_kernel<__nv_bfloat16, __nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_self);
     cudaFuncSetAttribute(local_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_local);
   }
   if (desc->precision == DSG_PRECISION_BF16) TRY_CREATE(dsg_tc_create(e));
@@ -279,7 +281,7 @@ extern "C" void dsg_engine_destroy(dsg_engine* e) {
   cudaSetDevice(e->d.device);
   dsg_tc_destroy(e);
   void* ptrs[] = {e->wslab, e->te, e->TW, e->Wxp, e->bxp, e->cs_local, e->emb1, e->cvec, e->enc, e->cond, e->h, e->xs,
-                  e->qkv, e->att, e->ff, e->tmp, e->x0, e->tsel, e->clip_ids, e->d_k, e->coef, e->tmap, e->dbg};
+                  e->qkv, e->att, e->ff, e->tmp, e->x0, e->tsel, e->clip_ids, e->d_k, e->d_loop, e->coef, e->tmap, e->dbg};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (Stage& s : e->stage) if (s.p) cudaFree(s.p);
   for (ProfSpan& sp : e->prof_spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
@@ -377,9 +379,10 @@ static int debug_snap(dsg_engine* e, int slot, int B, cudaStream_t st) {
   return DSG_OK;
 }
 
-int launch_local_attention(dsg_engine* e, int B, const float* h, float* xs, const int* tsel, StepRef step, cudaStream_t st) {
+int launch_local_attention(dsg_engine* e, int B, const float* h, long long h_clip_stride, int h_row0, float* xs,
+                           __nv_bfloat16* xsb, const int* tsel, StepRef step, cudaStream_t st) {
   LocalAttnArgs a;
-  a.h = h; a.xs = xs; a.emb1 = e->emb1; a.te = e->te; a.tsel = tsel; a.tmap = e->tmap; a.step = step;
+  a.h = h; a.h_clip_stride = h_clip_stride; a.h_row0 = h_row0; a.xs = xs; a.xsb = xsb; a.emb1 = e->emb1; a.te = e->te; a.tsel = tsel; a.tmap = e->tmap; a.step = step;
   a.cs = e->cs_local; a.T = e->d.n_poses; a.D = e->d.latent_dim; a.heads = e->d.local_heads; a.window = e->d.local_window;
   local_attention_kernel<<<B * e->d.local_heads, 128, e->smem_local, st>>>(a);
   e->launches++;
@@ -387,9 +390,17 @@ int launch_local_attention(dsg_engine* e, int B, const float* h, float* xs, cons
   return DSG_OK;
 }
 
+int launch_self_attention_bf16(dsg_engine* e, int B, const __nv_bfloat16* qkv, __nv_bfloat16* out, cudaStream_t st) {
+  SelfAttnArgs<__nv_bfloat16, __nv_bfloat16> sa{qkv, out, e->S, e->d.latent_dim, e->d.num_heads};
+  self_attention_kernel<__nv_bfloat16, __nv_bfloat16><<<B * e->d.num_heads, 256, e->smem_self, st>>>(sa);
+  e->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return DSG_OK;
+}
+
 int launch_self_attention(dsg_engine* e, int B, const float* qkv, float* out, cudaStream_t st) {
-  SelfAttnArgs sa{qkv, out, e->S, e->d.latent_dim, e->d.num_heads};
-  self_attention_kernel<<<B * e->d.num_heads, 256, e->smem_self, st>>>(sa);
+  SelfAttnArgs<float, float> sa{qkv, out, e->S, e->d.latent_dim, e->d.num_heads};
+  self_attention_kernel<float, float><<<B * e->d.num_heads, 256, e->smem_self, st>>>(sa);
   e->launches++;
   CUDA_TRY(cudaGetLastError());
   return DSG_OK;
@@ -406,7 +417,7 @@ static int denoise_f32(dsg_engine* e, int B, const float* x, const int* tsel, St
     g.tvec = e->TW; g.tvec_ld = D; g.tsel = tsel; g.tmap = e->tmap; g.step = step;
     PROF(e, PT_GEMM_IN, st, launch_gemm_f32(e, g, true, false, st));
   }
-  PROF(e, PT_LOCAL_ATTN, st, launch_local_attention(e, B, e->h, e->xs, tsel, step, st));
+  PROF(e, PT_LOCAL_ATTN, st, launch_local_attention(e, B, e->h, (long long)T * D, 0, e->xs, nullptr, tsel, step, st));
   TRY(debug_snap(e, 0, B, st));
   const int M = B * S;
   for (int l = 0; l < d.num_layers; ++l) {
@@ -464,7 +475,7 @@ extern "C" int dsg_denoise(dsg_engine* e, int32_t B, const float* x, const int32
 // --------------------------------------------------------------------------------------------------
 // posterior step, sampling loop, stitching
 // --------------------------------------------------------------------------------------------------
-static int elementwise_grid(const dsg_engine* e, long long quads) {
+int elementwise_grid(const dsg_engine* e, long long quads) {
   const long long want = (quads + 255) / 256;
   const long long cap = (long long)e->num_sms * 8;       // a multiple of the SM count, grid-stride inside
   return (int)(want < cap ? (want > 0 ? want : 1) : cap);
@@ -574,6 +585,15 @@ int dsg_run_steps(dsg_engine* e, int B, float* xd, int n_run, int first_index, u
   return DSG_OK;
 }
 
+int dsg_upload_loop_params(dsg_engine* e, int first_index, uint64_t seed, int segment, cudaStream_t st) {
+  LoopParams lp;
+  memset(&lp, 0, sizeof lp);
+  lp.k = 0; lp.first_index = first_index;
+  lp.key0 = (uint32_t)(seed & 0xffffffffu); lp.key1 = (uint32_t)(seed >> 32); lp.segment = (uint32_t)segment;
+  CUDA_TRY(cudaMemcpyAsync(e->d_loop, &lp, sizeof lp, cudaMemcpyHostToDevice, st));   // pageable source: staged before return
+  return DSG_OK;
+}
+
 extern "C" int dsg_stitch_segment(dsg_engine* e, int32_t B, const float* prev_tail, float* sample, int32_t smoothing,
                                   void* stream) {
   if (!e || !prev_tail || !sample) return dsg_fail(DSG_ERR_BAD_SHAPE, "null argument");
@@ -620,7 +640,11 @@ extern "C" int64_t dsg_debug_read(dsg_engine* e, const char* name, int32_t B, fl
   if (!strcmp(name, "h_in")) {
     const int64_t n = (int64_t)B * T * D;
     if (capacity < n) return dsg_fail(DSG_ERR_BAD_SHAPE, "capacity");
-    CUDA_TRY(cudaMemcpy(dst, e->h, n * sizeof(float), cudaMemcpyDefault));
+    if (e->d.precision == DSG_PRECISION_BF16)    // tensor-core path keeps h as [B,S,D] with the token slot at row 0
+      CUDA_TRY(cudaMemcpy2D(dst, (size_t)T * D * sizeof(float), dsg_tc_h(e) + D, (size_t)S * D * sizeof(float),
+                            (size_t)T * D * sizeof(float), B, cudaMemcpyDefault));
+    else
+      CUDA_TRY(cudaMemcpy(dst, e->h, n * sizeof(float), cudaMemcpyDefault));
     return n;
   }
   if (!e->debug) return dsg_fail(DSG_ERR_STATE, "call dsg_debug_read(e, \"enable\", ...) before the denoise call");
@@ -660,7 +684,7 @@ extern "C" int dsg_profile_read(dsg_engine* e, int32_t tag, int64_t* count, doub
 
 extern "C" const char* dsg_profile_tag_name(int32_t tag) {
   static const char* names[PT_COUNT] = {"gemm_in", "local_attention", "gemm_qkv", "self_attention", "gemm_outproj",
-                                        "layernorm", "gemm_ff1", "gemm_ff2", "gemm_head_posterior", "posterior", "other"};
+                                        "layernorm", "gemm_ff1", "gemm_ff2", "gemm_head_posterior", "posterior", "noise", "other"};
   return (tag >= 0 && tag < PT_COUNT) ? names[tag] : nullptr;
 }
 

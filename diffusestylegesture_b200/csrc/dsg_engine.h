@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "../../include/dsg.h"
+#include <cuda_bf16.h>
 #include "dsg_common.cuh"
 
 int dsg_fail(int code, const char* fmt, ...);
@@ -33,7 +34,7 @@ struct Stage { void* p = nullptr; size_t cap = 0; };
 
 // kernel classes for the optional per-kernel event timing (dsg_profile)
 enum ProfTag { PT_GEMM_IN = 0, PT_LOCAL_ATTN, PT_GEMM_QKV, PT_SELF_ATTN, PT_GEMM_OUTPROJ, PT_LAYERNORM, PT_GEMM_FF1,
-               PT_GEMM_FF2, PT_GEMM_HEAD, PT_POSTERIOR, PT_OTHER, PT_COUNT };
+               PT_GEMM_FF2, PT_GEMM_HEAD, PT_POSTERIOR, PT_NOISE, PT_OTHER, PT_COUNT };
 struct ProfSpan { int tag; cudaEvent_t a, b; };
 struct dsg_tc_state;
 
@@ -58,6 +59,7 @@ struct dsg_engine {
   int* tsel = nullptr;
   long long* clip_ids = nullptr;
   std::vector<long long> h_clip_ids;
+  LoopParams* d_loop = nullptr;      // device loop state for graph replay
   int* d_k = nullptr;
   size_t smem_self = 0, smem_local = 0;
   // debug taps
@@ -92,8 +94,12 @@ struct GemmF32Args;
 int launch_gemm_f32(dsg_engine* e, const GemmF32Args& g, bool a_m_contig, bool swap_mn, cudaStream_t st);
 int launch_layernorm(dsg_engine* e, const float* in, float* out, const float* gamma, const float* beta, int rows, int D,
                      cudaStream_t st);
-int launch_local_attention(dsg_engine* e, int B, const float* h, float* xs, const int* tsel, StepRef step, cudaStream_t st);
+int launch_local_attention(dsg_engine* e, int B, const float* h, long long h_clip_stride, int h_row0, float* xs,
+                           __nv_bfloat16* xsb, const int* tsel, StepRef step, cudaStream_t st);
 int launch_self_attention(dsg_engine* e, int B, const float* qkv, float* out, cudaStream_t st);
+int launch_self_attention_bf16(dsg_engine* e, int B, const __nv_bfloat16* qkv, __nv_bfloat16* out, cudaStream_t st);
+int elementwise_grid(const dsg_engine* e, long long quads);
+int dsg_upload_loop_params(dsg_engine* e, int first_index, uint64_t seed, int segment, cudaStream_t st);
 int launch_posterior(dsg_engine* e, int B, float* x, const float* x0, StepRef step, int index_imm, int draw_imm,
                      uint64_t seed, int segment, cudaStream_t st);
 int dsg_denoise_step(dsg_engine* e, int B, const float* x, const int* tsel, StepRef step, float* out, cudaStream_t st);
@@ -102,5 +108,6 @@ int dsg_run_steps(dsg_engine* e, int B, float* xd, int n_run, int first_index, u
 // tensor-core path (dsg_tc.cu)
 int dsg_tc_create(dsg_engine* e);
 void dsg_tc_destroy(dsg_engine* e);
+const float* dsg_tc_h(dsg_engine* e);
 int dsg_tc_denoise(dsg_engine* e, int B, const float* x, const int* tsel, StepRef step, float* out, cudaStream_t st);
 int dsg_tc_run_steps(dsg_engine* e, int B, float* xd, int n_run, int first_index, uint64_t seed, int segment, cudaStream_t st);

@@ -2,7 +2,13 @@
 // shared with the tensor-core path.  Each kernel names the reference code it stands for
 // (paths relative to /root/reference).
 #pragma once
+#include <cuda_bf16.h>
 #include "dsg_common.cuh"
+
+DSG_DEVINL float ldf(const float* p) { return *p; }
+DSG_DEVINL float ldf(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+DSG_DEVINL void stf(float* p, float v) { *p = v; }
+DSG_DEVINL void stf(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
 
 // ---------------------------------------------------------------------------------------------------
 // Generic strided SGEMM  C[m,n] = act( sum_k A[m,k] * B[n,k] + bias[n] + clipvec[clip(m)][n]
@@ -170,8 +176,10 @@ __global__ void __launch_bounds__(256) layernorm_rows_kernel(const float* __rest
 // rope tables: cs[pos][i] = (cos, sin)(pos * 10000^(-2i/hd)), i < hd/2.
 // ---------------------------------------------------------------------------------------------------
 struct LocalAttnArgs {
-  const float* h;          // [B,T,D]  input_process2 output
+  const float* h;          // input_process2 output: frame f of clip b at h + b*h_clip_stride + (f + h_row0)*D
+  long long h_clip_stride; int h_row0;
   float* xs;               // [B,S,D]
+  __nv_bfloat16* xsb;      // optional bf16 copy of xs (A operand of the first in_proj GEMM), nullable
   const float* emb1;       // [B,D]    style/seed embedding (step-invariant)
   const float* te;         // [n_t,D]  timestep-embedding table
   const int* tsel; const int* tmap; StepRef step;
@@ -186,7 +194,7 @@ __global__ void __launch_bounds__(128) local_attention_kernel(const LocalAttnArg
   float* orow = smem + a.T * ldz;                // [4 warps][hd]
   const int clip = blockIdx.x / a.heads, head = blockIdx.x - clip * a.heads;
   const int S = a.T + 1;
-  const float* hb = a.h + (long long)clip * a.T * a.D + head * hd;
+  const float* hb = a.h + (long long)clip * a.h_clip_stride + (long long)a.h_row0 * a.D + head * hd;
   for (int e = threadIdx.x; e < a.T * half; e += blockDim.x) {
     const int f = e / half, i = e - f * half;
     const float z1 = hb[(long long)f * a.D + i], z2 = hb[(long long)f * a.D + i + half];
@@ -195,10 +203,13 @@ __global__ void __launch_bounds__(128) local_attention_kernel(const LocalAttnArg
     z[f * ldz + i + half] = z2 * c.x + z1 * c.y;
   }
   float* xb = a.xs + (long long)clip * S * a.D + head * hd;
+  __nv_bfloat16* xbb = a.xsb ? a.xsb + (long long)clip * S * a.D + head * hd : nullptr;
   if (threadIdx.x < hd) {
     const int row = a.tsel ? a.tsel[clip] : a.tmap[a.step.index()];
     const int col = head * hd + threadIdx.x;
-    xb[threadIdx.x] = a.emb1[(long long)clip * a.D + col] + a.te[(long long)row * a.D + col];
+    const float tokv = a.emb1[(long long)clip * a.D + col] + a.te[(long long)row * a.D + col];
+    xb[threadIdx.x] = tokv;
+    if (xbb) xbb[threadIdx.x] = __float2bfloat16_rn(tokv);
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
@@ -228,8 +239,13 @@ __global__ void __launch_bounds__(128) local_attention_kernel(const LocalAttnArg
     for (int i = lane; i < half; i += 32) {
       const float2 c = a.cs[(f + 1) * half + i];
       const float o1 = ow[i], o2 = ow[i + half];
-      xb[(long long)(f + 1) * a.D + i] = o1 * c.x - o2 * c.y;
-      xb[(long long)(f + 1) * a.D + i + half] = o2 * c.x + o1 * c.y;
+      const float r1 = o1 * c.x - o2 * c.y, r2 = o2 * c.x + o1 * c.y;
+      xb[(long long)(f + 1) * a.D + i] = r1;
+      xb[(long long)(f + 1) * a.D + i + half] = r2;
+      if (xbb) {
+        xbb[(long long)(f + 1) * a.D + i] = __float2bfloat16_rn(r1);
+        xbb[(long long)(f + 1) * a.D + i + half] = __float2bfloat16_rn(r2);
+      }
     }
     __syncwarp();
   }
@@ -240,9 +256,11 @@ __global__ void __launch_bounds__(128) local_attention_kernel(const LocalAttnArg
 // softmax over all S keys, no mask; mdm.py:79-86, 233).  qkv [B*S, 3D] (q | k | v), out [B*S, D].
 // One CTA per (clip, head); K padded to hd+1 in shared memory (lane j reads row j: conflict-free).
 // ---------------------------------------------------------------------------------------------------
-struct SelfAttnArgs { const float* qkv; float* out; int S, D, heads; };
+template <typename TIn, typename TOut>
+struct SelfAttnArgs { const TIn* qkv; TOut* out; int S, D, heads; };
 
-__global__ void __launch_bounds__(256) self_attention_kernel(const SelfAttnArgs a) {
+template <typename TIn, typename TOut>
+__global__ void __launch_bounds__(256) self_attention_kernel(const SelfAttnArgs<TIn, TOut> a) {
   extern __shared__ float smem[];
   const int hd = a.D / a.heads, ldk = hd + 1;
   const int nwarps = blockDim.x >> 5;
@@ -252,11 +270,11 @@ __global__ void __launch_bounds__(256) self_attention_kernel(const SelfAttnArgs 
   float* qs = Vs + a.S * hd;             // [nwarps][hd]
   float* ps = qs + nwarps * hd;          // [nwarps][Spad]
   const int clip = blockIdx.x / a.heads, head = blockIdx.x - clip * a.heads;
-  const float* base = a.qkv + (long long)clip * a.S * 3 * a.D + head * hd;
+  const TIn* base = a.qkv + (long long)clip * a.S * 3 * a.D + head * hd;
   for (int e = threadIdx.x; e < a.S * hd; e += blockDim.x) {
     const int j = e / hd, d = e - j * hd;
-    Ks[j * ldk + d] = base[(long long)j * 3 * a.D + a.D + d];
-    Vs[j * hd + d] = base[(long long)j * 3 * a.D + 2 * a.D + d];
+    Ks[j * ldk + d] = ldf(base + (long long)j * 3 * a.D + a.D + d);
+    Vs[j * hd + d] = ldf(base + (long long)j * 3 * a.D + 2 * a.D + d);
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -264,7 +282,7 @@ __global__ void __launch_bounds__(256) self_attention_kernel(const SelfAttnArgs 
   float* q = qs + warp * hd;
   float* p = ps + warp * Spad;
   for (int i = warp; i < a.S; i += nwarps) {
-    for (int d = lane; d < hd; d += 32) q[d] = base[(long long)i * 3 * a.D + d] * scale;
+    for (int d = lane; d < hd; d += 32) q[d] = ldf(base + (long long)i * 3 * a.D + d) * scale;
     __syncwarp();
     float mx = -3.402823466e+38f;
     for (int j = lane; j < a.S; j += 32) {
@@ -279,11 +297,11 @@ __global__ void __launch_bounds__(256) self_attention_kernel(const SelfAttnArgs 
     for (int j = lane; j < a.S; j += 32) { const float e = expf(p[j] - mx); p[j] = e; sum += e; }
     const float inv = 1.0f / warp_sum(sum);
     __syncwarp();
-    float* o = a.out + ((long long)clip * a.S + i) * a.D + head * hd;
+    TOut* o = a.out + ((long long)clip * a.S + i) * a.D + head * hd;
     for (int d = lane; d < hd; d += 32) {
       float acc = 0.f;
       for (int j = 0; j < a.S; ++j) acc = fmaf(p[j], Vs[j * hd + d], acc);
-      o[d] = acc * inv;
+      stf(o + d, acc * inv);
     }
     __syncwarp();
   }

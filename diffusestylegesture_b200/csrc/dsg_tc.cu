@@ -1,14 +1,380 @@
 // Tensor-core (tcgen05 / TMEM / TMA) path of the engine — DSG_PRECISION_BF16.
-#include "dsg_engine.h"
+//
+// One denoiser call = 1 + 1 + 5*L + 1 (+1) kernels (L = 8 -> 44), every Linear a tcgen05 GEMM with its
+// consumer fused into the epilogue (dsg_tc_gemm.cuh); activations stay in L2-resident bf16 buffers, the residual
+// stream / LayerNorm / posterior stay fp32.  The 1000-step loop replays ONE captured CUDA graph of a step
+// (device-side step counter), with the data-independent noise draw on a forked branch.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
 
+#include <vector>
+
+#include "dsg_engine.h"
+#include "dsg_tc_gemm.cuh"
+#include "dsg_tc_kernels.cuh"
+
+using bf16 = __nv_bfloat16;
+using namespace tc;
+
+struct dsg_tc_state {
+  int Jpad = 0, Rpad = 0;
+  bf16 *Wxp = nullptr, *Wout = nullptr;
+  std::vector<bf16*> Wqkv, Wo, W1, W2;
+  bf16 *xb = nullptr, *xsb = nullptr, *qkvb = nullptr, *attb = nullptr, *ffb = nullptr;
+  float *hS = nullptr, *z = nullptr, *xloop = nullptr;
+  CUtensorMap tm_xb, tm_xsb, tm_attb, tm_ffb, tm_Wxp, tm_Wout;
+  std::vector<CUtensorMap> tm_Wqkv, tm_Wo, tm_W1, tm_W2;
+  // graph replay
+  cudaStream_t main = nullptr, side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_in = nullptr, ev_out = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  int graph_B = 0, graph_sampler = -1;
+  int nodes_per_step = 0;
+};
+
+// ---------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode = nullptr;
+
+static int get_encode() {
+  if (g_encode) return DSG_OK;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+  if (!fn || q != cudaDriverEntryPointSuccess) return dsg_fail(DSG_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+  g_encode = (EncodeTiledFn)fn;
+  return DSG_OK;
+}
+
+// bf16 row-major [rows, cols] -> 2-D tensor map with a (box_rows x 64) box and 128-byte swizzle
+static int make_tmap(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  TRY(get_encode());
+  if (cols % 8) return dsg_fail(DSG_ERR_BAD_SHAPE, "tensor map: row length %llu not a multiple of 8 bf16", (unsigned long long)cols);
+  const cuuint64_t gdim[2] = {cols, rows};
+  const cuuint64_t gstride[1] = {cols * sizeof(bf16)};
+  const cuuint32_t box[2] = {(cuuint32_t)BK, box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return dsg_fail(DSG_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu", (int)r,
+                                         (unsigned long long)rows, (unsigned long long)cols);
+  return DSG_OK;
+}
+
+template <int BN, int STAGES, int EPI>
+static int launch_tc(dsg_engine* e, const CUtensorMap& a, const CUtensorMap& b, const TcEpiArgs& ep, int n_tiles, cudaStream_t st) {
+  static bool configured = false;
+  constexpr int smem = TcSmem<BN, STAGES>::TOTAL;
+  if (!configured) {
+    CUDA_TRY(cudaFuncSetAttribute(tc_gemm_kernel<BN, STAGES, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  dim3 grid((ep.M + BM - 1) / BM, n_tiles);
+  tc_gemm_kernel<BN, STAGES, EPI><<<grid, 256, smem, st>>>(a, b, ep);
+  e->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return DSG_OK;
+}
+
+template <typename T>
+static int dalloc0(T** p, size_t n) {
+  CUDA_TRY(cudaMalloc((void**)p, n * sizeof(T)));
+  CUDA_TRY(cudaMemset(*p, 0, n * sizeof(T)));
+  return DSG_OK;
+}
+
+static int pack_w(const float* src, bf16* dst, int rows, int cols, long long ld, int rows_pad, int cols_pad) {
+  pack_weight_bf16_kernel<<<296, 256>>>(src, dst, rows, cols, ld, rows_pad, cols_pad);
+  CUDA_TRY(cudaGetLastError());
+  return DSG_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
 int dsg_tc_create(dsg_engine* e) {
-  (void)e;
-  return dsg_fail(DSG_ERR_UNSUPPORTED, "DSG_PRECISION_BF16 is not built yet");
+  const dsg_model_desc& d = e->d;
+  if (d.latent_dim != 256)
+    return dsg_fail(DSG_ERR_UNSUPPORTED, "DSG_PRECISION_BF16 currently covers latent_dim 256 (ZEGGS); D = %d runs on the fp32 engine",
+                    d.latent_dim);
+  if (d.ff_size % 256) return dsg_fail(DSG_ERR_UNSUPPORTED, "ff_size must be a multiple of 256 for the bf16 path");
+  dsg_tc_state* t = new dsg_tc_state();
+  e->tc = t;
+  const int D = d.latent_dim, F = d.ff_size, J = d.njoints, S = e->S, L = d.num_layers, MB = d.max_batch;
+  t->Jpad = (J + 127) / 128 * 128;
+  t->Rpad = (MB * S + BM - 1) / BM * BM;
+  const int Jpad = t->Jpad, Rpad = t->Rpad;
+  TRY(dalloc0(&t->Wxp, (size_t)D * Jpad));
+  TRY(dalloc0(&t->Wout, (size_t)Jpad * D));
+  TRY(pack_w(e->Wxp, t->Wxp, D, J, J, D, Jpad));
+  TRY(pack_w(e->w[W_OUT_W], t->Wout, J, D, D, Jpad, D));
+  t->Wqkv.resize(L); t->Wo.resize(L); t->W1.resize(L); t->W2.resize(L);
+  t->tm_Wqkv.resize(L); t->tm_Wo.resize(L); t->tm_W1.resize(L); t->tm_W2.resize(L);
+  for (int l = 0; l < L; ++l) {
+    float* const* w = &e->w[W_LAYER0 + 12 * l];
+    TRY(dalloc0(&t->Wqkv[l], (size_t)3 * D * D)); TRY(pack_w(w[L_INPROJ_W], t->Wqkv[l], 3 * D, D, D, 3 * D, D));
+    TRY(dalloc0(&t->Wo[l], (size_t)D * D));       TRY(pack_w(w[L_OUTPROJ_W], t->Wo[l], D, D, D, D, D));
+    TRY(dalloc0(&t->W1[l], (size_t)F * D));       TRY(pack_w(w[L_FF1_W], t->W1[l], F, D, D, F, D));
+    TRY(dalloc0(&t->W2[l], (size_t)D * F));       TRY(pack_w(w[L_FF2_W], t->W2[l], D, F, F, D, F));
+    TRY(make_tmap(&t->tm_Wqkv[l], t->Wqkv[l], 3 * D, D, 256));
+    TRY(make_tmap(&t->tm_Wo[l], t->Wo[l], D, D, 256));
+    TRY(make_tmap(&t->tm_W1[l], t->W1[l], F, D, 256));
+    TRY(make_tmap(&t->tm_W2[l], t->W2[l], D, F, 256));
+  }
+  TRY(dalloc0(&t->xb, (size_t)Rpad * Jpad));
+  TRY(dalloc0(&t->xsb, (size_t)Rpad * D));
+  TRY(dalloc0(&t->qkvb, (size_t)Rpad * 3 * D));
+  TRY(dalloc0(&t->attb, (size_t)Rpad * D));
+  TRY(dalloc0(&t->ffb, (size_t)Rpad * F));
+  TRY(dalloc0(&t->hS, (size_t)Rpad * D));
+  TRY(dalloc0(&t->z, (size_t)MB * J * d.n_poses));
+  TRY(dalloc0(&t->xloop, (size_t)MB * J * d.n_poses));
+  TRY(make_tmap(&t->tm_xb, t->xb, Rpad, Jpad, BM));
+  TRY(make_tmap(&t->tm_xsb, t->xsb, Rpad, D, BM));
+  TRY(make_tmap(&t->tm_attb, t->attb, Rpad, D, BM));
+  TRY(make_tmap(&t->tm_ffb, t->ffb, Rpad, F, BM));
+  TRY(make_tmap(&t->tm_Wxp, t->Wxp, D, Jpad, 256));
+  TRY(make_tmap(&t->tm_Wout, t->Wout, Jpad, D, 128));
+  CUDA_TRY(cudaStreamCreateWithFlags(&t->main, cudaStreamNonBlocking));
+  CUDA_TRY(cudaStreamCreateWithFlags(&t->side, cudaStreamNonBlocking));
+  CUDA_TRY(cudaEventCreateWithFlags(&t->ev_fork, cudaEventDisableTiming));
+  CUDA_TRY(cudaEventCreateWithFlags(&t->ev_join, cudaEventDisableTiming));
+  CUDA_TRY(cudaEventCreateWithFlags(&t->ev_in, cudaEventDisableTiming));
+  CUDA_TRY(cudaEventCreateWithFlags(&t->ev_out, cudaEventDisableTiming));
+  return DSG_OK;
 }
-void dsg_tc_destroy(dsg_engine* e) { (void)e; }
-int dsg_tc_denoise(dsg_engine*, int, const float*, const int*, StepRef, float*, cudaStream_t) {
-  return dsg_fail(DSG_ERR_UNSUPPORTED, "DSG_PRECISION_BF16 is not built yet");
+
+const float* dsg_tc_h(dsg_engine* e) { return e->tc ? e->tc->hS : nullptr; }
+
+void dsg_tc_destroy(dsg_engine* e) {
+  dsg_tc_state* t = e->tc;
+  if (!t) return;
+  if (t->exec) cudaGraphExecDestroy(t->exec);
+  void* ptrs[] = {t->Wxp, t->Wout, t->xb, t->xsb, t->qkvb, t->attb, t->ffb, t->hS, t->z, t->xloop};
+  for (void* p : ptrs) if (p) cudaFree(p);
+  for (auto& v : {t->Wqkv, t->Wo, t->W1, t->W2}) for (bf16* p : v) if (p) cudaFree(p);
+  if (t->main) cudaStreamDestroy(t->main);
+  if (t->side) cudaStreamDestroy(t->side);
+  for (cudaEvent_t ev : {t->ev_fork, t->ev_join, t->ev_in, t->ev_out}) if (ev) cudaEventDestroy(ev);
+  delete t;
+  e->tc = nullptr;
 }
-int dsg_tc_run_steps(dsg_engine*, int, float*, int, int, uint64_t, int, cudaStream_t) {
-  return dsg_fail(DSG_ERR_UNSUPPORTED, "DSG_PRECISION_BF16 is not built yet");
+
+// ---------------------------------------------------------------------------------------------------
+static int tc_pack_x(dsg_engine* e, int B, const float* x, cudaStream_t st) {
+  dsg_tc_state* t = e->tc;
+  dim3 grid((e->d.njoints + 31) / 32, (e->d.n_poses + 31) / 32, B);
+  pack_x_bf16_kernel<<<grid, 256, 0, st>>>(x, t->xb, e->d.njoints, e->d.n_poses, e->S, t->Jpad);
+  e->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return DSG_OK;
+}
+
+static int tc_noise(dsg_engine* e, int B, StepRef step, cudaStream_t st) {
+  NoiseArgs a{e->tc->z, e->clip_ids, step, B, (long long)e->d.njoints * e->d.n_poses, e->sampler};
+  noise_tile_kernel<<<elementwise_grid(e, (a.per_clip >> 2) * B), 256, 0, st>>>(a);
+  e->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return DSG_OK;
+}
+
+static int tc_debug_snap(dsg_engine* e, int slot, int B, cudaStream_t st) {
+  if (!e->debug) return DSG_OK;
+  const size_t n = (size_t)B * e->S * e->d.latent_dim;
+  CUDA_TRY(cudaMemcpyAsync(e->dbg + (size_t)slot * e->d.max_batch * e->S * e->d.latent_dim, e->xs, n * sizeof(float),
+                           cudaMemcpyDeviceToDevice, st));
+  return DSG_OK;
+}
+
+// self-attention: mma.sync kernel (S <= 96, head dim 64); DSG_ATTN=simt selects the CUDA-core kernel (debugging)
+static int tc_attention(dsg_engine* e, int B, cudaStream_t st) {
+  dsg_tc_state* t = e->tc;
+  static const bool simt = getenv("DSG_ATTN") && !strcmp(getenv("DSG_ATTN"), "simt");
+  const int hd = e->d.latent_dim / e->d.num_heads;
+  if (simt || hd != 64 || e->S > 96) return launch_self_attention_bf16(e, B, t->qkvb, t->attb, st);
+  const float scale_log2e = 1.4426950408889634f / sqrtf((float)hd);
+  self_attention_mma_kernel<6><<<B * e->d.num_heads, 192, 0, st>>>(t->qkvb, t->attb, e->S, e->d.latent_dim, e->d.num_heads, scale_log2e);
+  e->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return DSG_OK;
+}
+
+// everything of one denoiser call up to (not including) the head GEMM
+static int tc_body(dsg_engine* e, int B, const int* tsel, StepRef step, cudaStream_t st) {
+  dsg_tc_state* t = e->tc;
+  const dsg_model_desc& d = e->d;
+  const int D = d.latent_dim, F = d.ff_size, S = e->S, T = d.n_poses, M = B * S;
+  TcEpiArgs ep;
+  memset(&ep, 0, sizeof ep);
+  ep.M = M; ep.S = S; ep.T = T; ep.step = step;
+  {  // h = Wxp x_t + cond + TW[t]
+    TcEpiArgs a = ep;
+    a.N = D; a.K = t->Jpad; a.out = t->hS; a.cond = e->cond; a.TW = e->TW; a.tsel = tsel; a.tmap = e->tmap;
+    PROF(e, PT_GEMM_IN, st, (launch_tc<256, 4, EPI_IN>(e, t->tm_xb, t->tm_Wxp, a, 1, st)));
+  }
+  PROF(e, PT_LOCAL_ATTN, st, launch_local_attention(e, B, t->hS, (long long)S * D, 1, e->xs, t->xsb, tsel, step, st));
+  TRY(tc_debug_snap(e, 0, B, st));
+  for (int l = 0; l < d.num_layers; ++l) {
+    float* const* w = &e->w[W_LAYER0 + 12 * l];
+    {
+      TcEpiArgs a = ep;
+      a.N = 3 * D; a.K = D; a.bias = w[L_INPROJ_B]; a.out = t->qkvb; a.ldc = 3 * D;
+      PROF(e, PT_GEMM_QKV, st, (launch_tc<256, 4, EPI_BF16>(e, t->tm_xsb, t->tm_Wqkv[l], a, 3 * D / 256, st)));
+    }
+    PROF(e, PT_SELF_ATTN, st, tc_attention(e, B, st));
+    {
+      TcEpiArgs a = ep;
+      a.N = D; a.K = D; a.bias = w[L_OUTPROJ_B]; a.xs = e->xs; a.xsb = t->xsb; a.gamma = w[L_N1_W]; a.beta = w[L_N1_B];
+      PROF(e, PT_GEMM_OUTPROJ, st, (launch_tc<256, 4, EPI_LN>(e, t->tm_attb, t->tm_Wo[l], a, 1, st)));
+    }
+    {
+      TcEpiArgs a = ep;
+      a.N = F; a.K = D; a.bias = w[L_FF1_B]; a.out = t->ffb; a.ldc = F;
+      PROF(e, PT_GEMM_FF1, st, (launch_tc<256, 4, EPI_GELU>(e, t->tm_xsb, t->tm_W1[l], a, F / 256, st)));
+    }
+    {
+      TcEpiArgs a = ep;
+      a.N = D; a.K = F; a.bias = w[L_FF2_B]; a.xs = e->xs; a.xsb = t->xsb; a.gamma = w[L_N2_W]; a.beta = w[L_N2_B];
+      PROF(e, PT_GEMM_FF2, st, (launch_tc<256, 4, EPI_LN>(e, t->tm_ffb, t->tm_W2[l], a, 1, st)));
+    }
+    TRY(tc_debug_snap(e, l + 1, B, st));
+  }
+  return DSG_OK;
+}
+
+// OutputProcess (+ posterior when head_mode == 0)
+static int tc_head(dsg_engine* e, int B, float* x, StepRef step, int head_mode, float* out, cudaStream_t st) {
+  dsg_tc_state* t = e->tc;
+  const dsg_model_desc& d = e->d;
+  TcEpiArgs a;
+  memset(&a, 0, sizeof a);
+  a.M = B * e->S; a.N = d.njoints; a.K = d.latent_dim; a.S = e->S; a.T = d.n_poses; a.step = step;
+  a.bias = e->w[W_OUT_B]; a.x = x; a.z = t->z; a.xb = t->xb; a.J = d.njoints; a.Jpad = t->Jpad; a.coef = e->coef;
+  a.sampler = e->sampler; a.head_mode = head_mode; a.out = out;
+  PROF(e, PT_GEMM_HEAD, st, (launch_tc<128, 4, EPI_HEAD>(e, t->tm_xsb, t->tm_Wout, a, t->Jpad / 128, st)));
+  return DSG_OK;
+}
+
+int dsg_tc_denoise(dsg_engine* e, int B, const float* x, const int* tsel, StepRef step, float* out, cudaStream_t st) {
+  TRY(tc_pack_x(e, B, x, st));
+  TRY(tc_body(e, B, tsel, step, st));
+  return tc_head(e, B, nullptr, step, 1, out, st);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// The hot loop.  Profiling / debug: plain launches on the caller's stream.  Otherwise: one captured step,
+// replayed n_run times on the engine's stream (the legacy default stream cannot be captured).
+// ---------------------------------------------------------------------------------------------------
+static int tc_capture(dsg_engine* e, int B) {
+  dsg_tc_state* t = e->tc;
+  float* xd = t->xloop;
+  if (t->exec) { cudaGraphExecDestroy(t->exec); t->exec = nullptr; }
+  const StepRef step{e->d_loop, 0, 0, 0, 0, 0};
+  const int64_t l0 = e->launches;
+  cudaGraph_t graph = nullptr;
+  CUDA_TRY(cudaStreamBeginCapture(t->main, cudaStreamCaptureModeThreadLocal));
+  int rc = DSG_OK;
+  do {
+    if (cudaEventRecord(t->ev_fork, t->main) != cudaSuccess || cudaStreamWaitEvent(t->side, t->ev_fork, 0) != cudaSuccess) { rc = DSG_ERR_CUDA; break; }
+    if ((rc = tc_noise(e, B, step, t->side))) break;
+    if (cudaEventRecord(t->ev_join, t->side) != cudaSuccess) { rc = DSG_ERR_CUDA; break; }
+    if ((rc = tc_body(e, B, nullptr, step, t->main))) break;
+    if (cudaStreamWaitEvent(t->main, t->ev_join, 0) != cudaSuccess) { rc = DSG_ERR_CUDA; break; }
+    if ((rc = tc_head(e, B, xd, step, 0, nullptr, t->main))) break;
+    bump_step_kernel<<<1, 1, 0, t->main>>>(e->d_loop);
+    e->launches++;
+  } while (0);
+  const cudaError_t ce = cudaStreamEndCapture(t->main, &graph);
+  if (rc) { if (graph) cudaGraphDestroy(graph); if (rc == DSG_ERR_CUDA) dsg_fail(rc, "graph capture failed: %s", cudaGetErrorString(cudaGetLastError())); return rc; }
+  if (ce != cudaSuccess) return dsg_fail(DSG_ERR_CUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(ce));
+  t->nodes_per_step = (int)(e->launches - l0);
+  e->launches = l0;
+  const cudaError_t ci = cudaGraphInstantiate(&t->exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (ci != cudaSuccess) return dsg_fail(DSG_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(ci));
+  t->graph_B = B; t->graph_sampler = e->sampler;
+  e->graph_valid = true;
+  return DSG_OK;
+}
+
+int dsg_tc_run_steps(dsg_engine* e, int B, float* xd, int n_run, int first_index, uint64_t seed, int segment, cudaStream_t st) {
+  dsg_tc_state* t = e->tc;
+  if (e->profiling || e->debug) {
+    TRY(tc_pack_x(e, B, xd, st));
+    for (int k = 0; k < n_run; ++k) {
+      const StepRef step{nullptr, k, first_index, (uint32_t)(seed & 0xffffffffu), (uint32_t)(seed >> 32), (uint32_t)segment};
+      TRY(tc_body(e, B, nullptr, step, st));
+      PROF(e, PT_NOISE, st, tc_noise(e, B, step, st));
+      TRY(tc_head(e, B, xd, step, 0, nullptr, st));
+    }
+    return DSG_OK;
+  }
+  // hand over from the caller's stream to the engine's stream
+  CUDA_TRY(cudaEventRecord(t->ev_in, st));
+  CUDA_TRY(cudaStreamWaitEvent(t->main, t->ev_in, 0));
+  // the graph works on an engine-owned copy of x, so one instantiation serves every segment / caller buffer
+  const size_t xbytes = (size_t)B * e->d.njoints * e->d.n_poses * sizeof(float);
+  CUDA_TRY(cudaMemcpyAsync(t->xloop, xd, xbytes, cudaMemcpyDeviceToDevice, t->main));
+  TRY(dsg_upload_loop_params(e, first_index, seed, segment, t->main));
+  TRY(tc_pack_x(e, B, t->xloop, t->main));
+  int k_start = 0;
+  if (!e->graph_valid || !t->exec || t->graph_B != B || t->graph_sampler != e->sampler) {
+    // first step outside the capture: every kernel is loaded / configured before the stream goes into capture mode
+    const StepRef step{e->d_loop, 0, 0, 0, 0, 0};
+    TRY(tc_noise(e, B, step, t->main));
+    TRY(tc_body(e, B, nullptr, step, t->main));
+    TRY(tc_head(e, B, t->xloop, step, 0, nullptr, t->main));
+    bump_step_kernel<<<1, 1, 0, t->main>>>(e->d_loop);
+    e->launches++;
+    CUDA_TRY(cudaGetLastError());
+    k_start = 1;
+    if (n_run > 1) TRY(tc_capture(e, B));
+  }
+  for (int k = k_start; k < n_run; ++k) CUDA_TRY(cudaGraphLaunch(t->exec, t->main));
+  e->launches += (int64_t)t->nodes_per_step * (n_run - k_start);
+  CUDA_TRY(cudaMemcpyAsync(xd, t->xloop, xbytes, cudaMemcpyDeviceToDevice, t->main));
+  CUDA_TRY(cudaEventRecord(t->ev_out, t->main));
+  CUDA_TRY(cudaStreamWaitEvent(st, t->ev_out, 0));
+  return DSG_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Stand-alone check of the tcgen05 GEMM (tests/test_gpu_tc.py): C = bf16(A) * bf16(W)^T + bias, fp32 out.
+// ---------------------------------------------------------------------------------------------------
+extern "C" int dsg_selftest_gemm(int32_t device, int32_t bn, int32_t M, int32_t N, int32_t K, const float* A, const float* W,
+                                 const float* bias, float* C) {
+  if (!A || !W || !C || M <= 0 || N <= 0 || K <= 0 || (K % 8)) return dsg_fail(DSG_ERR_BAD_SHAPE, "selftest_gemm: bad arguments");
+  if (bn != 128 && bn != 256) return dsg_fail(DSG_ERR_BAD_SHAPE, "bn must be 128 or 256");
+  CUDA_TRY(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) return dsg_fail(DSG_ERR_BAD_ARCH, "sm_%d%d: tcgen05 needs sm_100", prop.major, prop.minor);
+  const int Mp = (M + BM - 1) / BM * BM, Np = (N + bn - 1) / bn * bn;
+  float *dA = nullptr, *dW = nullptr, *dB = nullptr, *dC = nullptr;
+  bf16 *bA = nullptr, *bW = nullptr;
+  CUDA_TRY(cudaMalloc(&dA, (size_t)M * K * 4)); CUDA_TRY(cudaMalloc(&dW, (size_t)N * K * 4));
+  CUDA_TRY(cudaMalloc(&dC, (size_t)M * N * 4)); CUDA_TRY(cudaMalloc(&dB, (size_t)N * 4));
+  CUDA_TRY(cudaMalloc(&bA, (size_t)Mp * K * 2)); CUDA_TRY(cudaMalloc(&bW, (size_t)Np * K * 2));
+  CUDA_TRY(cudaMemcpy(dA, A, (size_t)M * K * 4, cudaMemcpyDefault));
+  CUDA_TRY(cudaMemcpy(dW, W, (size_t)N * K * 4, cudaMemcpyDefault));
+  if (bias) CUDA_TRY(cudaMemcpy(dB, bias, (size_t)N * 4, cudaMemcpyDefault));
+  TRY(pack_w(dA, bA, M, K, K, Mp, K));
+  TRY(pack_w(dW, bW, N, K, K, Np, K));
+  CUtensorMap ta, tb;
+  TRY(make_tmap(&ta, bA, Mp, K, BM));
+  TRY(make_tmap(&tb, bW, Np, K, bn));
+  TcEpiArgs ep;
+  memset(&ep, 0, sizeof ep);
+  ep.M = M; ep.N = N; ep.K = K; ep.bias = bias ? dB : nullptr; ep.out = dC; ep.ldc = N;
+  dsg_engine fake;
+  if (bn == 128) TRY((launch_tc<128, 4, EPI_F32>(&fake, ta, tb, ep, Np / 128, 0)));
+  else TRY((launch_tc<256, 4, EPI_F32>(&fake, ta, tb, ep, Np / 256, 0)));
+  CUDA_TRY(cudaDeviceSynchronize());
+  CUDA_TRY(cudaMemcpy(C, dC, (size_t)M * N * 4, cudaMemcpyDefault));
+  cudaFree(dA); cudaFree(dW); cudaFree(dB); cudaFree(dC); cudaFree(bA); cudaFree(bW);
+  return DSG_OK;
 }

@@ -1,0 +1,377 @@
+// tcgen05 GEMM for sm_100a:  D[TMEM, fp32] = A[smem, bf16, K-major] * W[smem, bf16, K-major]^T
+//   - operands staged by TMA (cp.async.bulk.tensor.2d, 128-byte swizzle) through a STAGES-deep mbarrier ring,
+//   - one elected thread issues tcgen05.mma (UMMA 128 x BN x 16, cta_group::1), accumulator in tensor memory,
+//   - four epilogue warps read the accumulator with tcgen05.ld (32 lanes x 32 columns per instruction) and
+//     apply the fused epilogue of the Linear they stand for (see TcEpi below).
+// Warp roles (256 threads): 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 3 = idle, 4..7 = epilogue
+// (epilogue warp w owns TMEM lanes 32*(w%4) .. +31 = accumulator rows).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include "dsg_common.cuh"
+
+namespace tc {
+
+constexpr int BM = 128;          // UMMA_M (cta_group::1)
+constexpr int BK = 64;           // 64 bf16 = 128 B = one swizzle-128B row
+constexpr int UMMA_K = 16;       // fixed for 16-bit inputs
+
+enum TcEpi {
+  EPI_F32 = 0,      // C fp32 [M, ldc] = acc + bias                                       (self-test / generic)
+  EPI_IN = 1,       // h[b,s,:] = acc + cond[b,s-1,:] + TW[t,:]     InputProcess+input_process2 (mdm.py:196-206)
+  EPI_BF16 = 2,     // bf16 [M, ldc] = acc + bias                    in_proj of self-attention
+  EPI_GELU = 3,     // bf16 [M, ldc] = gelu_erf(acc + bias)          linear1 + activation
+  EPI_LN = 4,       // xs = LayerNorm(acc + bias + xs) -> fp32 + bf16 copies   out_proj / linear2 + norm (post-norm layer)
+  EPI_HEAD = 5      // x0 = acc + bias; posterior update of x (fp32 [B,J,T]) + bf16 repack [B,S,Jpad]   OutputProcess + p_sample
+};
+
+struct TcEpiArgs {
+  int M, N, K;                 // logical GEMM sizes (N = valid output columns; tile columns beyond N are skipped)
+  const float* bias;           // [N]
+  // EPI_F32 / EPI_BF16 / EPI_GELU
+  void* out; int ldc;
+  // EPI_IN
+  const float* cond; const float* TW; const int* tsel; const int* tmap; StepRef step; int S, T;
+  // EPI_LN
+  float* xs; __nv_bfloat16* xsb; const float* gamma; const float* beta;
+  // EPI_HEAD
+  float* x; const float* z; __nv_bfloat16* xb; int J, Jpad; const float4* coef; int sampler; int head_mode;  // 0 = posterior, 1 = write x0 to `out`
+};
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------
+DSG_DEVINL uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+DSG_DEVINL void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+DSG_DEVINL void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+DSG_DEVINL void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+DSG_DEVINL void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+DSG_DEVINL void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+DSG_DEVINL void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+DSG_DEVINL void tcgen05_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+DSG_DEVINL void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns of the accumulator -> 32 registers per thread (thread = row)
+DSG_DEVINL void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+DSG_DEVINL void tmem_st32(uint32_t taddr, const float* v) {
+  const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};\n" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
+      "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
+      "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
+// Shared-memory matrix descriptor for a K-major bf16 tile stored by TMA with SWIZZLE_128B:
+// rows of 128 B, 8-row (1024 B) swizzle atoms stacked along M/N.  Fields (cute::UMMA::SmemDescriptor):
+// [0,14) start>>4, [16,30) LBO>>4 (unused for swizzled K-major: 1), [32,46) SBO>>4 = 1024>>4, [46,48) version = 1,
+// [61,64) layout = 2 (SWIZZLE_128B).
+DSG_DEVINL uint64_t make_sw128_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// Instruction descriptor, kind::f16: D = fp32 (bits 4-5 = 1), A = B = bf16 (bits 7-9, 10-12 = 1), both K-major,
+// N>>3 at bits 17-22, M>>4 at bits 24-28 (cute::UMMA::InstrDescriptor).
+DSG_DEVINL constexpr uint32_t make_idesc_bf16(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+template <int BN, int STAGES>
+struct TcSmem {
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFF + (2 * STAGES + 1) * 8 + 16 + 1024;   // + alignment slack
+};
+
+DSG_DEVINL float posterior_apply(int sampler, const float4 c, float x0, float xt, float z, bool nz) {
+  if (sampler == 0) {
+    float r = __fadd_rn(__fmul_rn(c.x, x0), __fmul_rn(c.y, xt));
+    if (nz) r = __fadd_rn(r, __fmul_rn(c.z, z));
+    return r;
+  }
+  const float eps = __fdiv_rn(__fsub_rn(__fmul_rn(c.x, xt), x0), c.y);
+  return __fadd_rn(__fmul_rn(x0, c.z), __fmul_rn(c.w, eps));
+}
+
+template <int BN, int STAGES, int EPI>
+__global__ void __launch_bounds__(256, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcEpiArgs ep) {
+  using SM = TcSmem<BN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + SM::BAR_OFF);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  const int num_kb = (ep.K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)BN) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0 && lane == 0) {
+    // ===== TMA producer =====
+    for (int kb = 0; kb < num_kb; ++kb) {
+      const int s = kb % STAGES;
+      const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+      mbar_wait(&empty_bar[s], ph ^ 1u);
+      mbar_expect_tx(&full_bar[s], SM::STAGE_BYTES);
+      uint8_t* a_dst = smem + s * SM::STAGE_BYTES;
+      tma_load_2d(a_dst, &tmA, &full_bar[s], kb * BK, m0);
+      tma_load_2d(a_dst + SM::A_BYTES, &tmB, &full_bar[s], kb * BK, n0);
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===== MMA issuer =====
+    constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
+    for (int kb = 0; kb < num_kb; ++kb) {
+      const int s = kb % STAGES;
+      const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+      mbar_wait(&full_bar[s], ph);
+      tcgen05_fence_after();
+      const uint32_t a_addr = smem_u32(smem + s * SM::STAGE_BYTES);
+      const uint32_t b_addr = a_addr + SM::A_BYTES;
+#pragma unroll
+      for (int k = 0; k < BK / UMMA_K; ++k) {
+        const uint64_t adesc = make_sw128_desc(a_addr + k * UMMA_K * 2);
+        const uint64_t bdesc = make_sw128_desc(b_addr + k * UMMA_K * 2);
+        umma_bf16(tmem_base, adesc, bdesc, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+      }
+      tcgen05_commit(&empty_bar[s]);            // frees the smem stage when these MMAs retire
+    }
+    tcgen05_commit(tmem_full);                  // accumulator complete
+  } else if (warp >= 4) {
+    // ===== epilogue =====
+    mbar_wait(tmem_full, 0);
+    tcgen05_fence_after();
+    const int wq = warp & 3;
+    const int row = m0 + wq * 32 + lane;
+    const bool row_ok = row < ep.M;
+    const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16);
+    float v[32];
+
+    if constexpr (EPI == EPI_F32 || EPI == EPI_BF16 || EPI == EPI_GELU) {
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        tmem_ld32(taddr + c, v);
+        const int n = n0 + c;
+        if (!row_ok || n >= ep.N) continue;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float t = v[i] + (ep.bias ? __ldg(ep.bias + min(n + i, ep.N - 1)) : 0.f);
+          if (EPI == EPI_GELU) t = gelu_erf(t);
+          v[i] = t;
+        }
+        if constexpr (EPI == EPI_F32) {
+          float* o = reinterpret_cast<float*>(ep.out) + (long long)row * ep.ldc + n;
+          if (n + 32 <= ep.N && (ep.ldc & 3) == 0) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) if (n + i < ep.N) o[i] = v[i];
+          }
+        } else {
+          __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(ep.out) + (long long)row * ep.ldc + n;
+          if (n + 32 <= ep.N) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 8) {
+              __nv_bfloat162 p0 = __floats2bfloat162_rn(v[i], v[i + 1]), p1 = __floats2bfloat162_rn(v[i + 2], v[i + 3]);
+              __nv_bfloat162 p2 = __floats2bfloat162_rn(v[i + 4], v[i + 5]), p3 = __floats2bfloat162_rn(v[i + 6], v[i + 7]);
+              uint4 u;
+              u.x = *reinterpret_cast<uint32_t*>(&p0); u.y = *reinterpret_cast<uint32_t*>(&p1);
+              u.z = *reinterpret_cast<uint32_t*>(&p2); u.w = *reinterpret_cast<uint32_t*>(&p3);
+              *reinterpret_cast<uint4*>(o + i) = u;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) if (n + i < ep.N) o[i] = __float2bfloat16_rn(v[i]);
+          }
+        }
+      }
+    } else if constexpr (EPI == EPI_IN) {
+      // row = b*S + s; s == 0 is the token slot (filled by the local-attention kernel): skipped.
+      const int b = row / ep.S, s = row - b * ep.S;
+      const bool ok = row_ok && s > 0;
+      const float* cond = ep.cond + ((long long)b * ep.T + (s - 1)) * ep.N;
+      const int trow = ok ? (ep.tsel ? ep.tsel[b] : ep.tmap[ep.step.index()]) : 0;
+      const float* tw = ep.TW + (long long)trow * ep.N;
+      float* o = reinterpret_cast<float*>(ep.out) + (long long)row * ep.N;
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        tmem_ld32(taddr + c, v);
+        const int n = n0 + c;
+        if (!ok || n >= ep.N) continue;
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          const float4 cc = __ldg(reinterpret_cast<const float4*>(cond + n + i));
+          const float4 tt = __ldg(reinterpret_cast<const float4*>(tw + n + i));
+          *reinterpret_cast<float4*>(o + n + i) =
+              make_float4(v[i] + cc.x + tt.x, v[i + 1] + cc.y + tt.y, v[i + 2] + cc.z + tt.z, v[i + 3] + cc.w + tt.w);
+        }
+      }
+    } else if constexpr (EPI == EPI_LN) {
+      // full rows live in this CTA (BN == N == D): pass 1 adds bias + residual, parks v back in TMEM and
+      // accumulates the row statistics; pass 2 normalises and writes the fp32 residual stream + its bf16 copy.
+      float* xr = ep.xs + (long long)row * ep.N;
+      float sum = 0.f, sq = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        tmem_ld32(taddr + c, v);
+        if (row_ok) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            const float4 r4 = *reinterpret_cast<const float4*>(xr + c + i);
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + c + i));
+            v[i] += r4.x + b4.x; v[i + 1] += r4.y + b4.y; v[i + 2] += r4.z + b4.z; v[i + 3] += r4.w + b4.w;
+          }
+#pragma unroll
+          for (int i = 0; i < 32; ++i) { sum += v[i]; sq = fmaf(v[i], v[i], sq); }
+        }
+        tmem_st32(taddr + c, v);
+      }
+      const float mean = sum / (float)BN;
+      const float rstd = rsqrtf(fmaxf(sq / (float)BN - mean * mean, 0.f) + 1e-5f);
+      __nv_bfloat16* xbr = ep.xsb + (long long)row * ep.N;
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        tmem_ld32(taddr + c, v);
+        if (!row_ok) continue;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = (v[i] - mean) * rstd * __ldg(ep.gamma + c + i) + __ldg(ep.beta + c + i);
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(xr + c + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+          __nv_bfloat162 p0 = __floats2bfloat162_rn(v[i], v[i + 1]), p1 = __floats2bfloat162_rn(v[i + 2], v[i + 3]);
+          __nv_bfloat162 p2 = __floats2bfloat162_rn(v[i + 4], v[i + 5]), p3 = __floats2bfloat162_rn(v[i + 6], v[i + 7]);
+          uint4 u;
+          u.x = *reinterpret_cast<uint32_t*>(&p0); u.y = *reinterpret_cast<uint32_t*>(&p1);
+          u.z = *reinterpret_cast<uint32_t*>(&p2); u.w = *reinterpret_cast<uint32_t*>(&p3);
+          *reinterpret_cast<uint4*>(xbr + c + i) = u;
+        }
+      }
+    } else if constexpr (EPI == EPI_HEAD) {
+      // row = b*S + s -> frame f = s-1 of clip b; column n = joint channel j.  For fixed j a warp's 32 rows are
+      // 32 consecutive frames: x[b][j][f..f+31] is one coalesced 128-byte line.
+      const int b = row / ep.S, s = row - b * ep.S;
+      const bool ok = row_ok && s > 0;
+      const int f = s - 1;
+      const long long xoff = (long long)b * ep.J * ep.T + f;
+      __nv_bfloat16* xbr = ep.xb + (long long)row * ep.Jpad;
+      float4 cf = make_float4(0.f, 0.f, 0.f, 0.f);
+      bool nz = false;
+      if (ep.head_mode == 0) {
+        const int index = ep.step.index();
+        cf = ep.coef[index];
+        nz = (index != 0) && (ep.sampler == 0);
+      }
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        tmem_ld32(taddr + c, v);
+        const int n = n0 + c;
+        if (!ok || n >= ep.N) continue;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int j = n + i;
+          float r = 0.f;
+          if (j < ep.N) {
+            const float x0 = v[i] + __ldg(ep.bias + j);
+            const long long idx = xoff + (long long)j * ep.T;
+            if (ep.head_mode == 0) {
+              const float xt = ep.x[idx];
+              const float zz = nz ? __ldg(ep.z + idx) : 0.f;
+              r = posterior_apply(ep.sampler, cf, x0, xt, zz, nz);
+              ep.x[idx] = r;
+            } else {
+              reinterpret_cast<float*>(ep.out)[idx] = x0;
+            }
+          }
+          v[i] = r;
+        }
+        if (ep.head_mode == 0) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 8) {
+            __nv_bfloat162 p0 = __floats2bfloat162_rn(v[i], v[i + 1]), p1 = __floats2bfloat162_rn(v[i + 2], v[i + 3]);
+            __nv_bfloat162 p2 = __floats2bfloat162_rn(v[i + 4], v[i + 5]), p3 = __floats2bfloat162_rn(v[i + 6], v[i + 7]);
+            uint4 u;
+            u.x = *reinterpret_cast<uint32_t*>(&p0); u.y = *reinterpret_cast<uint32_t*>(&p1);
+            u.z = *reinterpret_cast<uint32_t*>(&p2); u.w = *reinterpret_cast<uint32_t*>(&p3);
+            if (n + i < ep.Jpad) *reinterpret_cast<uint4*>(xbr + n + i) = u;
+          }
+        }
+      }
+    }
+    tcgen05_fence_before();
+  }
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN) : "memory");
+  }
+}
+
+}  // namespace tc

@@ -19,7 +19,7 @@ SAMPLER = {"ddpm": 0, "ddim": 1}
 
 EXPORTS = ["dsg_engine_create", "dsg_engine_destroy", "dsg_set_schedule", "dsg_set_conditioning", "dsg_denoise",
            "dsg_posterior_step", "dsg_sample_loop", "dsg_stitch_segment", "dsg_kernel_launch_count",
-           "dsg_debug_read", "dsg_profile", "dsg_profile_read", "dsg_profile_tag_name", "dsg_last_error", "dsg_version"]
+           "dsg_debug_read", "dsg_profile", "dsg_profile_read", "dsg_profile_tag_name", "dsg_selftest_gemm", "dsg_last_error", "dsg_version"]
 
 
 class _Desc(ctypes.Structure):
@@ -66,6 +66,8 @@ def load_library(path=None):
     lib.dsg_profile_read.restype = ctypes.c_int
     lib.dsg_profile_tag_name.argtypes = [i32]
     lib.dsg_profile_tag_name.restype = ctypes.c_char_p
+    lib.dsg_selftest_gemm.argtypes = [i32, i32, i32, i32, i32, vp, vp, vp, vp]
+    lib.dsg_selftest_gemm.restype = ctypes.c_int
     lib.dsg_last_error.restype = ctypes.c_char_p
     lib.dsg_version.restype = ctypes.c_char_p
     if path is None:
@@ -94,6 +96,19 @@ def _ptr(t):
 
 def _stream(device):
     return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def selftest_gemm(A, W, bias=None, bn=128, device=0):
+    """C = bf16(A) @ bf16(W).T + bias on the tcgen05 GEMM (fp32 accumulate)."""
+    lib = load_library()
+    A = np.ascontiguousarray(A, dtype=np.float32)
+    W = np.ascontiguousarray(W, dtype=np.float32)
+    M, K = A.shape
+    N = W.shape[0]
+    C = np.empty((M, N), dtype=np.float32)
+    b = None if bias is None else np.ascontiguousarray(bias, dtype=np.float32)
+    _check(lib, lib.dsg_selftest_gemm(device, bn, M, N, K, _ptr(A), _ptr(W), _ptr(b), _ptr(C)))
+    return C
 
 
 class Engine:

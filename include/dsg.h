@@ -133,6 +133,11 @@ int dsg_profile(dsg_engine* e, int32_t enable);
 int dsg_profile_read(dsg_engine* e, int32_t tag, int64_t* count, double* total_ms);
 const char* dsg_profile_tag_name(int32_t tag);
 
+/* Stand-alone check of the tcgen05 GEMM building block (tests): C[M,N] = bf16(A[M,K]) * bf16(W[N,K])^T + bias, fp32
+ * accumulate and output.  bn = 128 or 256 (UMMA N); K a multiple of 8.  Host or device pointers. */
+int dsg_selftest_gemm(int32_t device, int32_t bn, int32_t M, int32_t N, int32_t K, const float* A, const float* W,
+                      const float* bias, float* C);
+
 const char* dsg_last_error(void);
 const char* dsg_version(void);
 

@@ -80,7 +80,7 @@ def test_posterior_step_matches_reference_arithmetic(eng):
         if index != 0:
             want = want + torch.tensor(float(coef[index, 2])) * z
         got = eng.posterior_step(x.clone().cuda(), x0.cuda(), index, SEED, clip_ids=clip_ids, segment=3, draw=draw)
-        assert _maxdiff(got, want) < 3e-6, index          # Box-Muller libm differences only
+        assert _maxdiff(got, want) < 6e-5, index          # MUFU-based Box-Muller vs libm (dsg_common.cuh: box_muller)
     got0 = eng.posterior_step(x.clone().cuda(), x0.cuda(), 0, SEED, clip_ids=clip_ids, segment=3, draw=1000)
     assert torch.equal(got0.cpu(), x0)                     # c1[0] = 1, c2[0] = 0, no noise at t = 0: exact
     # DDIM arithmetic
@@ -106,7 +106,8 @@ def test_noise_stream_matches_oracle_stream(eng):
     x = torch.zeros((2,) + shp).cuda()
     got = eng.posterior_step(x, torch.zeros_like(x), 5, 987654321012345, clip_ids=[3, 2 ** 33 + 1], segment=2, draw=77)
     want = O.noise_tensor(987654321012345, [3, 2 ** 33 + 1], 2, 77, shp)
-    assert _maxdiff(got, want) < 2e-6
+    assert _maxdiff(got, want) < 6e-5
+    assert float((got.cpu() - want).abs().mean()) < 1e-6
     assert abs(float(got.mean())) < 0.01 and abs(float(got.std()) - 1) < 0.01
 
 
