@@ -208,3 +208,30 @@ def test_bad_arguments_fail_loudly(eng):
     with pytest.raises(RuntimeError, match="timestep"):
         eng.denoise(torch.zeros(2, G.njoints, 1, G.n_poses), np.array([0, 1000], dtype=np.int32))
     assert eng.launches > 0
+
+
+@pytest.mark.parametrize("tag", ["beat", "twh"])
+def test_plus_variant_fp32_engine_vs_reference_golden(gold_dir, tag):
+    """DiffuseStyleGesture+ geometry (D = 384 / 512, T = 150, window 15, seed frames embedded per frame): denoiser and
+    a 20-step loop on the fp32 engine against the BEAT-TWH reference golden (every 4th channel is stored)."""
+    from diffusestylegesture_b200.config import BEAT_PLUS, TWH_PLUS
+    g = BEAT_PLUS if tag == "beat" else TWH_PLUS
+    gold = np.load(os.path.join(gold_dir, "beat_twh_plus.npz"))
+    sdg = synthetic_state_dict(g, seed=0)
+    e = Engine(g, sdg, device=0, max_batch=2, precision="fp32")
+    y = synthetic_conditioning(g, 2, segment=0)
+    y["seed"] = 0.5 * O.noise_tensor(SEED, [0, 1], 7, 99, (g.njoints, 1, g.n_seed))
+    x = O.noise_tensor(SEED, [0, 1], 0, 0, (g.njoints, 1, g.n_poses))
+    e.set_conditioning(y["style"], y["seed"], y["audio"])
+    out = e.denoise(x, gold[f"{tag}/t"])
+    assert _maxdiff(out[:, ::4], gold[f"{tag}/out_sub"]) < 3e-4
+    m = MDM(njoints=g.njoints, cond_mode='cross_local_attention4_style1_sample', audio_feat='wavlm', n_seed=g.n_seed,
+            latent_dim=g.latent_dim, style_dim=g.style_in, source_audio_dim=g.audio_dim,
+            audio_feat_dim_latent=g.audio_latent, precision="fp32", max_batch=2)
+    load_model_wo_clip(m, sdg)
+    m.to('cuda:0').eval()
+    d = create_gaussian_diffusion([20])
+    loop = d.p_sample_loop(m, (2, g.njoints, 1, g.n_poses), clip_denoised=False,
+                           model_kwargs={'y': dict(y, noise_seed=SEED, segment=0)})
+    assert _maxdiff(loop[:, ::4], gold[f"{tag}/loop20_sub"]) < 2e-3
+    e.close()

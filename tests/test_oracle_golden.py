@@ -103,3 +103,20 @@ def test_bvh_tail_full_clip_golden(gold_dir):
     assert pos.shape == (936, 75, 3)
     assert np.abs(pos - gold["positions"]).max() < 1e-4
     assert np.abs(eul - gold["rotations"]).max() < 2e-2
+
+
+@pytest.mark.parametrize("tag", ["beat", "twh"])
+def test_plus_variant_matches_reference(gold_dir, tag):
+    """DiffuseStyleGesture+ (BEAT-TWH-main/model/mdm.py:187-224, cross_local_attention4) — oracle vs reference golden."""
+    from diffusestylegesture_b200.config import BEAT_PLUS, TWH_PLUS
+    g = BEAT_PLUS if tag == "beat" else TWH_PLUS
+    gold = np.load(os.path.join(gold_dir, "beat_twh_plus.npz"))
+    sdg = synthetic_state_dict(g, seed=0)
+    y = synthetic_conditioning(g, 2, segment=0)
+    seed_pose = 0.5 * O.noise_tensor(SEED, [0, 1], 7, 99, (g.njoints, 1, g.n_seed))
+    assert np.array_equal(seed_pose[:, ::4].numpy(), gold[f"{tag}/seed_pose_sub"])
+    y["seed"] = seed_pose
+    x = O.noise_tensor(SEED, [0, 1], 0, 0, (g.njoints, 1, g.n_poses))
+    with torch.no_grad():
+        out = O.mdm_forward(sdg, g, x, torch.from_numpy(gold[f"{tag}/t"]), y)
+    assert float((out[:, ::4] - torch.from_numpy(gold[f"{tag}/out_sub"])).abs().max()) < 2e-5
