@@ -212,7 +212,8 @@ def main():
             precision = "bf16"
         except NotImplementedError:
             precision = "fp32"
-    B = args.batch or (64 if precision == "bf16" else 8)
+    # 212 clips x 89 token rows = 18,868 rows = 147.4 -> 148 M-tiles of 128 rows: exactly one wave of the 148 SMs
+    B = args.batch or (212 if precision == "bf16" else 8)
     model = make_model(precision, B)
     eng = model.get_engine(B)
     resp = '' if args.ddpm_steps == 1000 else [args.ddpm_steps]

@@ -260,7 +260,8 @@ extern "C" int dsg_engine_create(const dsg_model_desc* desc, const float* const*
     const int hdg = D / desc->num_heads;
     e->smem_self = (size_t)(S * (hdg + 1) + S * hdg + 8 * hdg + 8 * ((S + 31) & ~31)) * sizeof(float);
     const int hdl = D / desc->local_heads;
-    e->smem_local = (size_t)(T * (hdl + 1) + 4 * hdl) * sizeof(float);
+    e->local_threads = 32 * ((T + 7) / 8 < 16 ? (T + 7) / 8 : 16);        // ~8 query frames per warp
+    e->smem_local = (size_t)(T * (hdl + 1) + (e->local_threads / 32) * hdl) * sizeof(float);
     if (e->smem_self > 227 * 1024 || e->smem_local > 227 * 1024) {
       rc = dsg_fail(DSG_ERR_BAD_SHAPE, "sequence too long for the shared-memory attention kernels"); dsg_engine_destroy(e); return rc; }
     cudaFuncSetAttribute(self_attention_kernel<float, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_self);
@@ -384,7 +385,7 @@ int launch_local_attention(dsg_engine* e, int B, const float* h, long long h_cli
   LocalAttnArgs a;
   a.h = h; a.h_clip_stride = h_clip_stride; a.h_row0 = h_row0; a.xs = xs; a.xsb = xsb; a.emb1 = e->emb1; a.te = e->te; a.tsel = tsel; a.tmap = e->tmap; a.step = step;
   a.cs = e->cs_local; a.T = e->d.n_poses; a.D = e->d.latent_dim; a.heads = e->d.local_heads; a.window = e->d.local_window;
-  local_attention_kernel<<<B * e->d.local_heads, 128, e->smem_local, st>>>(a);
+  local_attention_kernel<<<B * e->d.local_heads, e->local_threads, e->smem_local, st>>>(a);
   e->launches++;
   CUDA_TRY(cudaGetLastError());
   return DSG_OK;

@@ -62,6 +62,7 @@ struct dsg_engine {
   LoopParams* d_loop = nullptr;      // device loop state for graph replay
   int* d_k = nullptr;
   size_t smem_self = 0, smem_local = 0;
+  int local_threads = 128;
   // debug taps
   bool debug = false;
   float* dbg = nullptr;

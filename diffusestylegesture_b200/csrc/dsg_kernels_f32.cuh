@@ -187,11 +187,11 @@ struct LocalAttnArgs {
   int T, D, heads, window;
 };
 
-__global__ void __launch_bounds__(128) local_attention_kernel(const LocalAttnArgs a) {
+__global__ void __launch_bounds__(512) local_attention_kernel(const LocalAttnArgs a) {
   extern __shared__ float smem[];
   const int hd = a.D / a.heads, half = hd >> 1, ldz = hd + 1;
   float* z = smem;                               // [T][hd+1]  rope'd h slice
-  float* orow = smem + a.T * ldz;                // [4 warps][hd]
+  float* orow = smem + a.T * ldz;                // [warps][hd]
   const int clip = blockIdx.x / a.heads, head = blockIdx.x - clip * a.heads;
   const int S = a.T + 1;
   const float* hb = a.h + (long long)clip * a.h_clip_stride + (long long)a.h_row0 * a.D + head * hd;

@@ -126,7 +126,8 @@ struct TcSmem {
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
-  static constexpr int TOTAL = BAR_OFF + (2 * STAGES + 1) * 8 + 16 + 1024;   // + alignment slack
+  static constexpr int RED_OFF = BAR_OFF + 128;                               // LayerNorm partials [2][128][2] fp32
+  static constexpr int TOTAL = RED_OFF + 2048 + 1024;                         // + alignment slack
 };
 
 DSG_DEVINL float posterior_apply(int sampler, const float4 c, float x0, float xt, float z, bool nz) {
@@ -139,6 +140,36 @@ DSG_DEVINL float posterior_apply(int sampler, const float4 c, float x0, float xt
   return __fadd_rn(__fmul_rn(x0, c.z), __fmul_rn(c.w, eps));
 }
 
+// erf to 1.5e-7 absolute (Abramowitz & Stegun 7.1.26) on MUFU.RCP / MUFU.EX2 — ~14 instructions instead of ~30 for
+// erff; far below the bf16 rounding of the value it feeds (F.gelu in nn.TransformerEncoderLayer, mdm.py:79-86).
+DSG_DEVINL float erf_fast(float x) {
+  const float ax = fabsf(x);
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, ax, 1.0f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float r = fmaf(-p * t, __expf(-ax * ax), 1.0f);
+  return copysignf(r, x);
+}
+DSG_DEVINL float gelu_fast(float x) { return 0.5f * x * (1.0f + erf_fast(x * 0.70710678118654752440f)); }
+
+DSG_DEVINL void store_bf16x32(__nv_bfloat16* o, const float* v) {
+#pragma unroll
+  for (int i = 0; i < 32; i += 8) {
+    __nv_bfloat162 p0 = __floats2bfloat162_rn(v[i], v[i + 1]), p1 = __floats2bfloat162_rn(v[i + 2], v[i + 3]);
+    __nv_bfloat162 p2 = __floats2bfloat162_rn(v[i + 4], v[i + 5]), p3 = __floats2bfloat162_rn(v[i + 6], v[i + 7]);
+    uint4 u;
+    u.x = *reinterpret_cast<uint32_t*>(&p0); u.y = *reinterpret_cast<uint32_t*>(&p1);
+    u.z = *reinterpret_cast<uint32_t*>(&p2); u.w = *reinterpret_cast<uint32_t*>(&p3);
+    *reinterpret_cast<uint4*>(o + i) = u;
+  }
+}
+
+// The epilogue runs on ALL 8 warps: warp w and warp w+4 share TMEM lane quarter w%4 (accumulator rows
+// 32*(w%4)..+31) and split the BN columns into interleaved 32-column chunks (even chunks: warps 0-3, odd: 4-7).
+// One epilogue warp per scheduler is dependent-issue bound; two per scheduler with 32 independent elements each
+// keep the ALU pipes busy.
 template <int BN, int STAGES, int EPI>
 __global__ void __launch_bounds__(256, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcEpiArgs ep) {
@@ -149,6 +180,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  float* red = reinterpret_cast<float*>(smem + SM::RED_OFF);     // [2 halves][128 rows][2] LayerNorm partials
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
@@ -203,170 +235,172 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tcgen05_commit(&empty_bar[s]);            // frees the smem stage when these MMAs retire
     }
     tcgen05_commit(tmem_full);                  // accumulator complete
-  } else if (warp >= 4) {
-    // ===== epilogue =====
-    mbar_wait(tmem_full, 0);
-    tcgen05_fence_after();
-    const int wq = warp & 3;
-    const int row = m0 + wq * 32 + lane;
-    const bool row_ok = row < ep.M;
-    const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16);
-    float v[32];
+  }
+  __syncwarp();
 
-    if constexpr (EPI == EPI_F32 || EPI == EPI_BF16 || EPI == EPI_GELU) {
+  // ===== epilogue (all 8 warps) =====
+  mbar_wait(tmem_full, 0);
+  tcgen05_fence_after();
+  const int wq = warp & 3, half = warp >> 2;
+  const int rloc = wq * 32 + lane;
+  const int row = m0 + rloc;
+  const bool row_ok = row < ep.M;
+  const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16);
+  float v[32];
+
+  if constexpr (EPI == EPI_F32 || EPI == EPI_BF16 || EPI == EPI_GELU) {
 #pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
-        tmem_ld32(taddr + c, v);
-        const int n = n0 + c;
-        if (!row_ok || n >= ep.N) continue;
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float t = v[i] + (ep.bias ? __ldg(ep.bias + min(n + i, ep.N - 1)) : 0.f);
-          if (EPI == EPI_GELU) t = gelu_erf(t);
-          v[i] = t;
-        }
-        if constexpr (EPI == EPI_F32) {
-          float* o = reinterpret_cast<float*>(ep.out) + (long long)row * ep.ldc + n;
-          if (n + 32 <= ep.N && (ep.ldc & 3) == 0) {
-#pragma unroll
-            for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) if (n + i < ep.N) o[i] = v[i];
-          }
-        } else {
-          __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(ep.out) + (long long)row * ep.ldc + n;
-          if (n + 32 <= ep.N) {
-#pragma unroll
-            for (int i = 0; i < 32; i += 8) {
-              __nv_bfloat162 p0 = __floats2bfloat162_rn(v[i], v[i + 1]), p1 = __floats2bfloat162_rn(v[i + 2], v[i + 3]);
-              __nv_bfloat162 p2 = __floats2bfloat162_rn(v[i + 4], v[i + 5]), p3 = __floats2bfloat162_rn(v[i + 6], v[i + 7]);
-              uint4 u;
-              u.x = *reinterpret_cast<uint32_t*>(&p0); u.y = *reinterpret_cast<uint32_t*>(&p1);
-              u.z = *reinterpret_cast<uint32_t*>(&p2); u.w = *reinterpret_cast<uint32_t*>(&p3);
-              *reinterpret_cast<uint4*>(o + i) = u;
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) if (n + i < ep.N) o[i] = __float2bfloat16_rn(v[i]);
-          }
-        }
-      }
-    } else if constexpr (EPI == EPI_IN) {
-      // row = b*S + s; s == 0 is the token slot (filled by the local-attention kernel): skipped.
-      const int b = row / ep.S, s = row - b * ep.S;
-      const bool ok = row_ok && s > 0;
-      const float* cond = ep.cond + ((long long)b * ep.T + (s - 1)) * ep.N;
-      const int trow = ok ? (ep.tsel ? ep.tsel[b] : ep.tmap[ep.step.index()]) : 0;
-      const float* tw = ep.TW + (long long)trow * ep.N;
-      float* o = reinterpret_cast<float*>(ep.out) + (long long)row * ep.N;
-#pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
-        tmem_ld32(taddr + c, v);
-        const int n = n0 + c;
-        if (!ok || n >= ep.N) continue;
+    for (int c = half * 32; c < BN; c += 64) {
+      tmem_ld32(taddr + c, v);
+      const int n = n0 + c;
+      if (!row_ok || n >= ep.N) continue;
+      if (n + 32 <= ep.N) {
 #pragma unroll
         for (int i = 0; i < 32; i += 4) {
-          const float4 cc = __ldg(reinterpret_cast<const float4*>(cond + n + i));
-          const float4 tt = __ldg(reinterpret_cast<const float4*>(tw + n + i));
-          *reinterpret_cast<float4*>(o + n + i) =
-              make_float4(v[i] + cc.x + tt.x, v[i + 1] + cc.y + tt.y, v[i + 2] + cc.z + tt.z, v[i + 3] + cc.w + tt.w);
+          const float4 b4 = ep.bias ? __ldg(reinterpret_cast<const float4*>(ep.bias + n + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
         }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) if (ep.bias && n + i < ep.N) v[i] += __ldg(ep.bias + n + i);
       }
-    } else if constexpr (EPI == EPI_LN) {
-      // full rows live in this CTA (BN == N == D): pass 1 adds bias + residual, parks v back in TMEM and
-      // accumulates the row statistics; pass 2 normalises and writes the fp32 residual stream + its bf16 copy.
-      float* xr = ep.xs + (long long)row * ep.N;
-      float sum = 0.f, sq = 0.f;
-#pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
-        tmem_ld32(taddr + c, v);
-        if (row_ok) {
+      if constexpr (EPI == EPI_GELU) {
 #pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            const float4 r4 = *reinterpret_cast<const float4*>(xr + c + i);
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + c + i));
-            v[i] += r4.x + b4.x; v[i + 1] += r4.y + b4.y; v[i + 2] += r4.z + b4.z; v[i + 3] += r4.w + b4.w;
-          }
+        for (int i = 0; i < 32; ++i) v[i] = gelu_fast(v[i]);
+      }
+      if constexpr (EPI == EPI_F32) {
+        float* o = reinterpret_cast<float*>(ep.out) + (long long)row * ep.ldc + n;
+        if (n + 32 <= ep.N && (ep.ldc & 3) == 0) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) { sum += v[i]; sq = fmaf(v[i], v[i], sq); }
+          for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) if (n + i < ep.N) o[i] = v[i];
         }
-        tmem_st32(taddr + c, v);
-      }
-      const float mean = sum / (float)BN;
-      const float rstd = rsqrtf(fmaxf(sq / (float)BN - mean * mean, 0.f) + 1e-5f);
-      __nv_bfloat16* xbr = ep.xsb + (long long)row * ep.N;
-#pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
-        tmem_ld32(taddr + c, v);
-        if (!row_ok) continue;
+      } else {
+        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(ep.out) + (long long)row * ep.ldc + n;
+        if (n + 32 <= ep.N) {
+          store_bf16x32(o, v);
+        } else {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = (v[i] - mean) * rstd * __ldg(ep.gamma + c + i) + __ldg(ep.beta + c + i);
-#pragma unroll
-        for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(xr + c + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-#pragma unroll
-        for (int i = 0; i < 32; i += 8) {
-          __nv_bfloat162 p0 = __floats2bfloat162_rn(v[i], v[i + 1]), p1 = __floats2bfloat162_rn(v[i + 2], v[i + 3]);
-          __nv_bfloat162 p2 = __floats2bfloat162_rn(v[i + 4], v[i + 5]), p3 = __floats2bfloat162_rn(v[i + 6], v[i + 7]);
-          uint4 u;
-          u.x = *reinterpret_cast<uint32_t*>(&p0); u.y = *reinterpret_cast<uint32_t*>(&p1);
-          u.z = *reinterpret_cast<uint32_t*>(&p2); u.w = *reinterpret_cast<uint32_t*>(&p3);
-          *reinterpret_cast<uint4*>(xbr + c + i) = u;
-        }
-      }
-    } else if constexpr (EPI == EPI_HEAD) {
-      // row = b*S + s -> frame f = s-1 of clip b; column n = joint channel j.  For fixed j a warp's 32 rows are
-      // 32 consecutive frames: x[b][j][f..f+31] is one coalesced 128-byte line.
-      const int b = row / ep.S, s = row - b * ep.S;
-      const bool ok = row_ok && s > 0;
-      const int f = s - 1;
-      const long long xoff = (long long)b * ep.J * ep.T + f;
-      __nv_bfloat16* xbr = ep.xb + (long long)row * ep.Jpad;
-      float4 cf = make_float4(0.f, 0.f, 0.f, 0.f);
-      bool nz = false;
-      if (ep.head_mode == 0) {
-        const int index = ep.step.index();
-        cf = ep.coef[index];
-        nz = (index != 0) && (ep.sampler == 0);
-      }
-#pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
-        tmem_ld32(taddr + c, v);
-        const int n = n0 + c;
-        if (!ok || n >= ep.N) continue;
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int j = n + i;
-          float r = 0.f;
-          if (j < ep.N) {
-            const float x0 = v[i] + __ldg(ep.bias + j);
-            const long long idx = xoff + (long long)j * ep.T;
-            if (ep.head_mode == 0) {
-              const float xt = ep.x[idx];
-              const float zz = nz ? __ldg(ep.z + idx) : 0.f;
-              r = posterior_apply(ep.sampler, cf, x0, xt, zz, nz);
-              ep.x[idx] = r;
-            } else {
-              reinterpret_cast<float*>(ep.out)[idx] = x0;
-            }
-          }
-          v[i] = r;
-        }
-        if (ep.head_mode == 0) {
-#pragma unroll
-          for (int i = 0; i < 32; i += 8) {
-            __nv_bfloat162 p0 = __floats2bfloat162_rn(v[i], v[i + 1]), p1 = __floats2bfloat162_rn(v[i + 2], v[i + 3]);
-            __nv_bfloat162 p2 = __floats2bfloat162_rn(v[i + 4], v[i + 5]), p3 = __floats2bfloat162_rn(v[i + 6], v[i + 7]);
-            uint4 u;
-            u.x = *reinterpret_cast<uint32_t*>(&p0); u.y = *reinterpret_cast<uint32_t*>(&p1);
-            u.z = *reinterpret_cast<uint32_t*>(&p2); u.w = *reinterpret_cast<uint32_t*>(&p3);
-            if (n + i < ep.Jpad) *reinterpret_cast<uint4*>(xbr + n + i) = u;
-          }
+          for (int i = 0; i < 32; ++i) if (n + i < ep.N) o[i] = __float2bfloat16_rn(v[i]);
         }
       }
     }
-    tcgen05_fence_before();
+  } else if constexpr (EPI == EPI_IN) {
+    // row = b*S + s; s == 0 is the token slot (filled by the local-attention kernel): skipped.
+    const int b = row / ep.S, s = row - b * ep.S;
+    const bool ok = row_ok && s > 0;
+    const float* cond = ep.cond + ((long long)b * ep.T + (s - 1)) * ep.N;
+    const int trow = ok ? (ep.tsel ? ep.tsel[b] : ep.tmap[ep.step.index()]) : 0;
+    const float* tw = ep.TW + (long long)trow * ep.N;
+    float* o = reinterpret_cast<float*>(ep.out) + (long long)row * ep.N;
+#pragma unroll 1
+    for (int c = half * 32; c < BN; c += 64) {
+      tmem_ld32(taddr + c, v);
+      const int n = n0 + c;
+      if (!ok || n >= ep.N) continue;
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        const float4 cc = __ldg(reinterpret_cast<const float4*>(cond + n + i));
+        const float4 tt = __ldg(reinterpret_cast<const float4*>(tw + n + i));
+        *reinterpret_cast<float4*>(o + n + i) =
+            make_float4(v[i] + cc.x + tt.x, v[i + 1] + cc.y + tt.y, v[i + 2] + cc.z + tt.z, v[i + 3] + cc.w + tt.w);
+      }
+    }
+  } else if constexpr (EPI == EPI_LN) {
+    // full rows live in this CTA (BN == N == D).  Pass 1 adds bias + residual, parks v back in TMEM and accumulates
+    // this warp's share of the row statistics; the two column halves meet through shared memory; pass 2 normalises
+    // and writes the fp32 residual stream + its bf16 copy.
+    float* xr = ep.xs + (long long)row * ep.N;
+    float sum = 0.f, sq = 0.f;
+#pragma unroll 1
+    for (int c = half * 32; c < BN; c += 64) {
+      tmem_ld32(taddr + c, v);
+      if (row_ok) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          const float4 r4 = *reinterpret_cast<const float4*>(xr + c + i);
+          const float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + c + i));
+          v[i] += r4.x + b4.x; v[i + 1] += r4.y + b4.y; v[i + 2] += r4.z + b4.z; v[i + 3] += r4.w + b4.w;
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) { sum += v[i]; sq = fmaf(v[i], v[i], sq); }
+      }
+      tmem_st32(taddr + c, v);
+    }
+    red[(half * 128 + rloc) * 2] = sum;
+    red[(half * 128 + rloc) * 2 + 1] = sq;
+    __syncthreads();
+    sum = red[rloc * 2] + red[(128 + rloc) * 2];
+    sq = red[rloc * 2 + 1] + red[(128 + rloc) * 2 + 1];
+    const float mean = sum / (float)BN;
+    const float rstd = rsqrtf(fmaxf(sq / (float)BN - mean * mean, 0.f) + 1e-5f);
+    __nv_bfloat16* xbr = ep.xsb + (long long)row * ep.N;
+#pragma unroll 1
+    for (int c = half * 32; c < BN; c += 64) {
+      tmem_ld32(taddr + c, v);
+      if (!row_ok) continue;
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        const float4 g4 = __ldg(reinterpret_cast<const float4*>(ep.gamma + c + i));
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.beta + c + i));
+        v[i] = (v[i] - mean) * rstd * g4.x + b4.x; v[i + 1] = (v[i + 1] - mean) * rstd * g4.y + b4.y;
+        v[i + 2] = (v[i + 2] - mean) * rstd * g4.z + b4.z; v[i + 3] = (v[i + 3] - mean) * rstd * g4.w + b4.w;
+      }
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(xr + c + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+      store_bf16x32(xbr + c, v);
+    }
+  } else if constexpr (EPI == EPI_HEAD) {
+    // row = b*S + s -> frame f = s-1 of clip b; column n = joint channel j.  For fixed j a warp's 32 rows are
+    // 32 consecutive frames: x[b][j][f..f+31] is one coalesced 128-byte line.  All loads of a chunk are issued
+    // before the first store (x is read-modify-written in place: the compiler cannot prove the stores do not alias).
+    const int b = row / ep.S, s = row - b * ep.S;
+    const bool ok = row_ok && s > 0;
+    const int f = s - 1;
+    const long long xoff = (long long)b * ep.J * ep.T + f;
+    __nv_bfloat16* xbr = ep.xb + (long long)row * ep.Jpad;
+    float4 cf = make_float4(0.f, 0.f, 0.f, 0.f);
+    bool nz = false;
+    if (ep.head_mode == 0) {
+      const int index = ep.step.index();
+      cf = ep.coef[index];
+      nz = (index != 0) && (ep.sampler == 0);
+    }
+#pragma unroll 1
+    for (int c = half * 32; c < BN; c += 64) {
+      tmem_ld32(taddr + c, v);
+      const int n = n0 + c;
+      if (!ok || n >= ep.N) continue;
+      const long long base = xoff + (long long)n * ep.T;
+      if (ep.head_mode == 0) {
+        float xt[32], zz[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) xt[i] = (n + i < ep.N) ? ep.x[base + (long long)i * ep.T] : 0.f;
+        if (nz) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) zz[i] = (n + i < ep.N) ? __ldg(ep.z + base + (long long)i * ep.T) : 0.f;
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) zz[i] = 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float x0 = v[i] + __ldg(ep.bias + min(n + i, ep.N - 1));
+          v[i] = (n + i < ep.N) ? posterior_apply(ep.sampler, cf, x0, xt[i], zz[i], nz) : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) if (n + i < ep.N) ep.x[base + (long long)i * ep.T] = v[i];
+        store_bf16x32(xbr + n, v);           // Jpad is a multiple of 32: the padded columns receive zeros
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (n + i < ep.N) reinterpret_cast<float*>(ep.out)[base + (long long)i * ep.T] = v[i] + __ldg(ep.bias + n + i);
+      }
+    }
   }
+  tcgen05_fence_before();
   __syncthreads();
   if (warp == 2) {
     tcgen05_fence_after();
