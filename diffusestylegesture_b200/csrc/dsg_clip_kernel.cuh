@@ -1,0 +1,722 @@
+// The clip kernel: ONE persistent CTA per clip runs the whole sampling loop of a segment — every DDPM step, every
+// layer — with the activations resident in shared / tensor memory and only the weights streaming in (TMA, L2-resident
+// bf16, 13.4 MB per step).  Clips are independent, so there is no inter-CTA synchronisation at
+// all: no kernel boundaries, no grid barriers, no activation traffic through L2.  ZEGGS geometry (D 256, F 1024,
+// 4 x 64 global heads, 8 x 32 local heads, window 11, T 88, J 1141) is compiled in.
+//
+// Warp roles (384 threads):  0 = TMA weight producer   1 = tcgen05.mma issuer   2,3 = noise pre-draw (Philox)
+//                            4..11 = 8 worker warps: A-operand staging, all epilogues, both attentions.
+// Tensor memory (512 columns) = 4 quarters of 128 fp32 columns (Q0..Q3), handed back and forth per op with
+// ready/free mbarriers.  Shared memory:
+//   XS  [128 x 256] bf16, UMMA K-major SWIZZLE_128B (4 k-tiles)  — the residual stream AND the A operand
+//   BUF [128 x 256] bf16, same format — A ring of the input GEMM / rope'd h for local attention /
+//                                        attention output (A of out_proj) / FFN hidden chunk (A of linear2)
+//   W   3 x 16 KB weight stages ([128 or 64 rows] x 64 k), TMA + mbarrier ring
+//   Qs/Ks/Vs [96][72] bf16 per-head staging for the mma.sync attention; LayerNorm partials; barriers.
+#pragma once
+#include "dsg_tc_gemm.cuh"
+#include "dsg_tc_kernels.cuh"
+
+namespace clip {
+using namespace tc;
+
+constexpr int D = 256, F = 1024, NH = 4, HD = 64, LH = 8, LHD = 32, WIN = 11, T = 88, S = 89, J = 1141, JPAD = 1152, NL = 8;
+constexpr int NS = 3;                       // weight ring stages
+constexpr int WSTAGE = 16384;               // [128 rows x 64 k] bf16
+constexpr int KT = 16384;                   // one A k-tile [128 x 64] bf16
+constexpr int OFF_XS = 0;
+constexpr int OFF_BUF = 4 * KT;
+constexpr int OFF_W = 8 * KT;
+constexpr int QLD = 72;                     // Qs/Ks/Vs row stride (bf16 elements): 16 B pad -> conflict-free ldmatrix
+constexpr int OFF_Q = OFF_W + NS * WSTAGE;
+constexpr int OFF_K = OFF_Q + 96 * QLD * 2;
+constexpr int OFF_V = OFF_K + 96 * QLD * 2;
+constexpr int OFF_RED = OFF_V + 96 * QLD * 2;
+constexpr int OFF_BAR = OFF_RED + 2048;
+constexpr int SMEM_BYTES = OFF_BAR + 512 + 1024;
+constexpr int ZLD = 264;                    // rope'd h staging row stride (bf16), lives in BUF: 104 rows x 528 B
+constexpr int ZROWS = 104;
+static_assert(ZROWS * ZLD * 2 <= 4 * KT, "Z staging must fit in BUF");
+static_assert(SMEM_BYTES <= 232448, "shared memory budget");
+
+// per-layer fp32 parameter block (biases, LayerNorm): offsets in floats
+constexpr int P_BQKV = 0, P_BO = 768, P_G1 = 1024, P_BE1 = 1280, P_B1 = 1536, P_B2 = 2560, P_G2 = 2816, P_BE2 = 3072, P_SIZE = 3328;
+// weight slab row map (K = 256 slab): layer l at l*2048: [qkv reordered per head 768 | out_proj 256 | linear1 1024]; pose head after the layers
+constexpr int R_LAYER = 2048, R_QKV = 0, R_WO = 768, R_W1 = 1024, R_HEAD = NL * R_LAYER;
+
+// barrier indices
+enum { B_WFULL = 0, B_WEMPTY = 3, B_AFULL = 6, B_AEMPTY = 10, B_ACCR = 14, B_ACCF = 18, B_XSR = 22, B_BUFR = 23, B_BUFF = 25,
+       B_ZR = 27, B_ZF = 28, B_COUNT = 29 };
+
+struct ClipParams {
+  float* x;                 // [B][J][T] fp32, in/out
+  float* z;                 // [B][J*T] fp32 noise scratch
+  const float* cond;        // [B][T][D]
+  const float* emb1;        // [B][D]
+  const float* te;          // [n_t][D]
+  const float* TW;          // [n_t][D]
+  const float2* cs;         // [S][16]  rope (cos, sin) for local head dim 32
+  const float* lparams;     // [NL][P_SIZE]
+  const float* bout;        // [JPAD]
+  const float4* coef;
+  const int* tmap;
+  const long long* clip_ids;
+  const LoopParams* lp;
+  int B, n_run, sampler;
+  float* dbg; long long dbg_slot; int debug;     // taps: dbg[slot * dbg_slot + (clip*S + s)*D + col]
+  long long* prof;          // optional [32] cycle counters written by CTA 0 (see PF_* below), nullable
+};
+
+DSG_DEVINL void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+DSG_DEVINL void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+DSG_DEVINL void workers_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+DSG_DEVINL void ldsm_x2(uint32_t& r0, uint32_t& r1, const void* p) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(a));
+}
+// byte offset of element (row r, column c) inside a [128 x 256] bf16 operand stored as 4 SWIZZLE_128B k-tiles
+DSG_DEVINL uint32_t a_off(int r, int c) {
+  return (uint32_t)((c >> 6) * KT + (r >> 3) * 1024 + (r & 7) * 128 + ((((c & 63) >> 3) ^ (r & 7)) << 4) + (c & 7) * 2);
+}
+DSG_DEVINL uint4 pack8(const float* v) {
+  uint4 u;
+  u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]); u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
+  return u;
+}
+DSG_DEVINL void unpack8(const uint4 u, float* v) {
+  const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { const float2 f = __bfloat1622float2(p[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+}
+
+// cycle counters (CTA 0): where each role spends its time
+enum { PF_TOTAL = 0, PF_MMA_WAIT_W, PF_MMA_WAIT_OTHER, PF_PROD_WAIT_EMPTY, PF_W_STAGE, PF_W_IN_WAIT, PF_W_IN_EPI, PF_W_LOCAL,
+       PF_W_QKV_WAIT, PF_W_ATT, PF_W_LN_WAIT, PF_W_LN, PF_W_GELU_WAIT, PF_W_GELU, PF_W_HEAD_WAIT, PF_W_HEAD, PF_W_ZWAIT, PF_COUNT };
+
+struct Phases {            // one phase bit per barrier, toggled on every completed wait
+  uint32_t bits;
+  DSG_DEVINL void wait(uint64_t* bars, int id) { mbar_wait(&bars[id], (bits >> id) & 1u); bits ^= 1u << id; }
+};
+
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(384, 1)
+clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152]   box 128 x 64
+            const __grid_constant__ CUtensorMap tm_w128,   // K=256 slab          box 128 x 64
+            const __grid_constant__ CUtensorMap tm_w64,    // K=256 slab          box  64 x 64
+            const __grid_constant__ CUtensorMap tm_w2,     // linear2 slab [NL*256, 1024]  box 128 x 64
+            const ClipParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + B_COUNT);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NS; ++i) { mbar_init(&bars[B_WFULL + i], 1); mbar_init(&bars[B_WEMPTY + i], 1); }
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(&bars[B_AFULL + i], 8); mbar_init(&bars[B_AEMPTY + i], 1);
+      mbar_init(&bars[B_ACCR + i], 1);  mbar_init(&bars[B_ACCF + i], 8);
+    }
+    mbar_init(&bars[B_XSR], 8);
+    for (int i = 0; i < 2; ++i) { mbar_init(&bars[B_BUFR + i], 8); mbar_init(&bars[B_BUFF + i], 1); }
+    mbar_init(&bars[B_ZR], 2); mbar_init(&bars[B_ZF], 8);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_in) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_w128) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_w64) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_w2) : "memory");
+  }
+  // zero the operand buffers once: rows that are never written (token slot of the A ring, rows >= S, Z pad rows) stay finite
+  for (int i = threadIdx.x; i < (OFF_W) / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
+  for (int i = threadIdx.x; i < (OFF_RED - OFF_Q) / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem + OFF_Q)[i] = make_uint4(0u, 0u, 0u, 0u);
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  fence_async_smem();
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const int first_index = P.lp->first_index;
+  const uint32_t key0 = P.lp->key0, key1 = P.lp->key1, segment = P.lp->segment;
+
+  if (warp == 0) {
+    // =================================================== TMA weight producer ===================================================
+    if (lane == 0) {
+      Phases ph{0x7u << B_WEMPTY};                 // "empty" barriers start free
+      int slot = 0;
+      long long t_wait = 0;
+      const bool prof = P.prof != nullptr && blockIdx.x == 0;
+      auto load = [&](const CUtensorMap* m, int row, int kcol, uint32_t bytes) {
+        const long long c0 = prof ? clock64() : 0;
+        ph.wait(bars, B_WEMPTY + slot);
+        if (prof) t_wait += clock64() - c0;
+        mbar_expect_tx(&bars[B_WFULL + slot], bytes);
+        tma_load_2d(smem + OFF_W + slot * WSTAGE, m, &bars[B_WFULL + slot], kcol, row);
+        slot = (slot + 1 == NS) ? 0 : slot + 1;
+      };
+      for (int clip = blockIdx.x; clip < P.B; clip += gridDim.x)
+        for (int k = 0; k < P.n_run; ++k) {
+          for (int kb = 0; kb < JPAD / 64; ++kb)
+            for (int nh = 0; nh < 2; ++nh) load(&tm_in, nh * 128, kb * 64, WSTAGE);
+          for (int l = 0; l < NL; ++l) {
+            const int rb = l * R_LAYER;
+            for (int h = 0; h < NH; ++h)
+              for (int part = 0; part < 3; ++part)
+                for (int kb = 0; kb < 4; ++kb) load(&tm_w64, rb + R_QKV + h * 192 + part * 64, kb * 64, WSTAGE / 2);
+            for (int nh = 0; nh < 2; ++nh)
+              for (int kb = 0; kb < 4; ++kb) load(&tm_w128, rb + R_WO + nh * 128, kb * 64, WSTAGE);
+            auto ff1 = [&](int c) { for (int kb = 0; kb < 4; ++kb) load(&tm_w128, rb + R_W1 + c * 128, kb * 64, WSTAGE); };
+            ff1(0); ff1(1);
+            for (int c = 0; c < 8; ++c) {
+              for (int nh = 0; nh < 2; ++nh)
+                for (int kb2 = 0; kb2 < 2; ++kb2) load(&tm_w2, l * 256 + nh * 128, c * 128 + kb2 * 64, WSTAGE);
+              if (c + 2 < 8) ff1(c + 2);
+            }
+          }
+          for (int t = 0; t < JPAD / 128; ++t)
+            for (int kb = 0; kb < 4; ++kb) load(&tm_w128, R_HEAD + t * 128, kb * 64, WSTAGE);
+        }
+      if (prof) P.prof[PF_PROD_WAIT_EMPTY] = t_wait;
+    }
+  } else if (warp == 1) {
+    // =================================================== MMA issuer ===================================================
+    if (lane == 0) {
+      Phases ph{(0xFu << B_ACCF)};                 // accumulators start free
+      int slot = 0;
+      const uint32_t xs_addr = smem_u32(smem + OFF_XS), buf_addr = smem_u32(smem + OFF_BUF), w_addr = smem_u32(smem + OFF_W);
+      constexpr uint32_t idesc128 = make_idesc_bf16(128, 128), idesc64 = make_idesc_bf16(128, 64);
+      // one weight tile: 4 UMMAs (K = 64) of A k-tile `a_tile` against the current stage
+      long long t_w = 0, t_o = 0;
+      const bool prof = P.prof != nullptr && blockIdx.x == 0;
+      const long long t_begin = clock64();
+      auto tile = [&](uint32_t a_tile, uint32_t d_col, uint32_t idesc, bool acc_first) {
+        const long long c0 = prof ? clock64() : 0;
+        ph.wait(bars, B_WFULL + slot);
+        if (prof) t_w += clock64() - c0;
+        tcgen05_fence_after();
+        const uint32_t b_tile = w_addr + slot * WSTAGE;
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+          umma_bf16(tmem + d_col, make_sw128_desc(a_tile + kk * 32), make_sw128_desc(b_tile + kk * 32), idesc, (acc_first || kk > 0) ? 1u : 0u);
+        tcgen05_commit(&bars[B_WEMPTY + slot]);
+        slot = (slot + 1 == NS) ? 0 : slot + 1;
+      };
+      auto owait = [&](int id) { const long long c0 = prof ? clock64() : 0; ph.wait(bars, id); if (prof) t_o += clock64() - c0; };
+      for (int clip = blockIdx.x; clip < P.B; clip += gridDim.x)
+        for (int k = 0; k < P.n_run; ++k) {
+          // ---- input GEMM: A k-blocks staged by the workers into the BUF ring, D = Q0|Q1
+          owait(B_ACCF + 0); owait(B_ACCF + 1);
+          for (int kb = 0; kb < JPAD / 64; ++kb) {
+            owait(B_AFULL + (kb & 3));
+            tcgen05_fence_after();
+            for (int nh = 0; nh < 2; ++nh) tile(buf_addr + (kb & 3) * KT, nh * 128, idesc128, kb > 0);
+            tcgen05_commit(&bars[B_AEMPTY + (kb & 3)]);
+          }
+          tcgen05_commit(&bars[B_ACCR + 0]); tcgen05_commit(&bars[B_ACCR + 1]);
+          for (int l = 0; l < NL; ++l) {
+            // ---- in_proj, one head at a time into alternating TMEM halves: q | k | v = 3 x 64 columns
+            owait(B_XSR);
+            tcgen05_fence_after();
+            for (int h = 0; h < NH; ++h) {
+              const int hb = h & 1;
+              owait(B_ACCF + 2 * hb); owait(B_ACCF + 2 * hb + 1);
+              tcgen05_fence_after();
+              for (int part = 0; part < 3; ++part)
+                for (int kb = 0; kb < 4; ++kb) tile(xs_addr + kb * KT, hb * 256 + part * 64, idesc64, kb > 0);
+              tcgen05_commit(&bars[B_ACCR + 2 * hb]); tcgen05_commit(&bars[B_ACCR + 2 * hb + 1]);
+            }
+            // ---- out_proj: A = attention output in BUF, D = Q0|Q1
+            owait(B_BUFR + 0); owait(B_BUFR + 1);
+            owait(B_ACCF + 0); owait(B_ACCF + 1);
+            tcgen05_fence_after();
+            for (int nh = 0; nh < 2; ++nh)
+              for (int kb = 0; kb < 4; ++kb) tile(buf_addr + kb * KT, nh * 128, idesc128, kb > 0);
+            tcgen05_commit(&bars[B_ACCR + 0]); tcgen05_commit(&bars[B_ACCR + 1]);
+            tcgen05_commit(&bars[B_BUFF + 0]); tcgen05_commit(&bars[B_BUFF + 1]);
+            // ---- FFN: linear1 in 8 chunks of 128 hidden units (D = Q2 / Q3 alternating), linear2 accumulates into Q0|Q1
+            owait(B_XSR);
+            tcgen05_fence_after();
+            auto ff1 = [&](int c) {
+              owait(B_ACCF + 2 + (c & 1));
+              tcgen05_fence_after();
+              for (int kb = 0; kb < 4; ++kb) tile(xs_addr + kb * KT, (2 + (c & 1)) * 128, idesc128, kb > 0);
+              tcgen05_commit(&bars[B_ACCR + 2 + (c & 1)]);
+            };
+            ff1(0); ff1(1);
+            for (int c = 0; c < 8; ++c) {
+              owait(B_BUFR + (c & 1));
+              if (c == 0) { owait(B_ACCF + 0); owait(B_ACCF + 1); }
+              tcgen05_fence_after();
+              for (int nh = 0; nh < 2; ++nh)
+                for (int kb2 = 0; kb2 < 2; ++kb2) tile(buf_addr + ((c & 1) * 2 + kb2) * KT, nh * 128, idesc128, c > 0 || kb2 > 0);
+              tcgen05_commit(&bars[B_BUFF + (c & 1)]);
+              if (c + 2 < 8) ff1(c + 2);
+            }
+            tcgen05_commit(&bars[B_ACCR + 0]); tcgen05_commit(&bars[B_ACCR + 1]);
+          }
+          // ---- pose head: 9 tiles of 128 joint channels, D rotates over the 4 quarters
+          owait(B_XSR);
+          tcgen05_fence_after();
+          for (int t = 0; t < JPAD / 128; ++t) {
+            owait(B_ACCF + (t & 3));
+            tcgen05_fence_after();
+            for (int kb = 0; kb < 4; ++kb) tile(xs_addr + kb * KT, (t & 3) * 128, idesc128, kb > 0);
+            tcgen05_commit(&bars[B_ACCR + (t & 3)]);
+          }
+        }
+      if (prof) { P.prof[PF_TOTAL] = clock64() - t_begin; P.prof[PF_MMA_WAIT_W] = t_w; P.prof[PF_MMA_WAIT_OTHER] = t_o; }
+    }
+  } else if (warp < 4) {
+    // =================================================== noise pre-draw ===================================================
+    Phases ph{1u << B_ZF};
+    const int nt = (warp - 2) * 32 + lane;           // 0..63
+    for (int clip = blockIdx.x; clip < P.B; clip += gridDim.x) {
+      const uint32_t cid = (uint32_t)P.clip_ids[clip];
+      float* zc = P.z + (long long)clip * J * T;
+      for (int k = 0; k < P.n_run; ++k) {
+        const int index = first_index - k;
+        if (index == 0 || P.sampler != 0) continue;
+        ph.wait(bars, B_ZF);
+        for (int q = nt; q < J * T / 4; q += 64)
+          *reinterpret_cast<float4*>(zc + 4 * q) = philox_normal4((uint32_t)q, (uint32_t)(1 + k), cid, segment, key0, key1);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars[B_ZR]);
+      }
+    }
+  } else {
+    // =================================================== workers ===================================================
+    const int ww = warp - 4;                         // 0..7
+    const int q4 = ww & 3, sub = ww >> 2;            // TMEM lane quarter (== warp % 4), column half
+    const int r = q4 * 32 + lane;                    // accumulator row == token slot s (row 0 = token, rows 1..88 = frames)
+    const int wt = threadIdx.x - 128;                // 0..255
+    const uint32_t tlane = tmem + ((uint32_t)(q4 * 32) << 16);
+    Phases ph{(0xFu << B_AEMPTY) | (0x3u << B_BUFF)};
+    __nv_bfloat16* Zs = reinterpret_cast<__nv_bfloat16*>(smem + OFF_BUF);
+    __nv_bfloat16* Qs = reinterpret_cast<__nv_bfloat16*>(smem + OFF_Q);
+    __nv_bfloat16* Ks = reinterpret_cast<__nv_bfloat16*>(smem + OFF_K);
+    __nv_bfloat16* Vs = reinterpret_cast<__nv_bfloat16*>(smem + OFF_V);
+    float* red = reinterpret_cast<float*>(smem + OFF_RED);
+    uint8_t* XS = smem + OFF_XS;
+    uint8_t* BUF = smem + OFF_BUF;
+    float v[32];
+    const bool prof = P.prof != nullptr && blockIdx.x == 0 && wt == 0;
+    long long pf[PF_COUNT];
+#pragma unroll
+    for (int i = 0; i < PF_COUNT; ++i) pf[i] = 0;
+    long long tmark = clock64();
+    auto lap = [&](int id) { if (prof) { const long long c = clock64(); pf[id] += c - tmark; tmark = c; } };
+
+    auto release_acc = [&](int qa, int qb, bool xs_ready, int buf_ready) {
+      tcgen05_fence_before();
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&bars[B_ACCF + qa]);
+        if (qb >= 0) mbar_arrive(&bars[B_ACCF + qb]);
+        if (xs_ready) mbar_arrive(&bars[B_XSR]);
+        if (buf_ready >= 0) mbar_arrive(&bars[B_BUFR + buf_ready]);
+      }
+    };
+    // residual + bias + LayerNorm on the accumulator in Q0|Q1, result -> XS (bf16).  Thread = (row, 128-column half).
+    auto layernorm_epilogue = [&](const float* bias, const float* gamma, const float* beta) {
+      ph.wait(bars, B_ACCR + 0); ph.wait(bars, B_ACCR + 1);
+      lap(PF_W_LN_WAIT);
+      tcgen05_fence_after();
+      float sum = 0.f, sq = 0.f;
+#pragma unroll 1
+      for (int c4 = 0; c4 < 4; ++c4) {
+        const int col0 = sub * 128 + c4 * 32;
+        tmem_ld32(tlane + col0, v);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float rs[8];
+          unpack8(*reinterpret_cast<const uint4*>(XS + a_off(r, col0 + i * 8)), rs);
+          const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + col0 + i * 8));
+          const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + col0 + i * 8 + 4));
+          v[i * 8 + 0] += rs[0] + b0.x; v[i * 8 + 1] += rs[1] + b0.y; v[i * 8 + 2] += rs[2] + b0.z; v[i * 8 + 3] += rs[3] + b0.w;
+          v[i * 8 + 4] += rs[4] + b1.x; v[i * 8 + 5] += rs[5] + b1.y; v[i * 8 + 6] += rs[6] + b1.z; v[i * 8 + 7] += rs[7] + b1.w;
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) { sum += v[i]; sq = fmaf(v[i], v[i], sq); }
+        tmem_st32(tlane + col0, v);
+      }
+      red[(sub * 128 + r) * 2] = sum; red[(sub * 128 + r) * 2 + 1] = sq;
+      workers_sync();
+      sum = red[r * 2] + red[(128 + r) * 2]; sq = red[r * 2 + 1] + red[(128 + r) * 2 + 1];
+      const float mean = sum * (1.0f / D);
+      const float rstd = rsqrtf(fmaxf(sq * (1.0f / D) - mean * mean, 0.f) + 1e-5f);
+#pragma unroll 1
+      for (int c4 = 0; c4 < 4; ++c4) {
+        const int col0 = sub * 128 + c4 * 32;
+        tmem_ld32(tlane + col0, v);
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma + col0 + i));
+          const float4 b4 = __ldg(reinterpret_cast<const float4*>(beta + col0 + i));
+          v[i] = (v[i] - mean) * rstd * g4.x + b4.x; v[i + 1] = (v[i + 1] - mean) * rstd * g4.y + b4.y;
+          v[i + 2] = (v[i + 2] - mean) * rstd * g4.z + b4.z; v[i + 3] = (v[i + 3] - mean) * rstd * g4.w + b4.w;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(XS + a_off(r, col0 + i * 8)) = pack8(v + i * 8);
+      }
+      workers_sync();                               // `red` is reused by the next LayerNorm
+      release_acc(0, 1, true, -1);
+      lap(PF_W_LN);
+    };
+    auto debug_dump = [&](int slot, int clip) {
+      if (!P.debug) return;
+      workers_sync();
+      if (r < S) {
+        float* o = P.dbg + (long long)slot * P.dbg_slot + ((long long)clip * S + r) * D + sub * 128;
+        for (int c8 = 0; c8 < 16; ++c8) {
+          float t8[8];
+          unpack8(*reinterpret_cast<const uint4*>(XS + a_off(r, sub * 128 + c8 * 8)), t8);
+          for (int i = 0; i < 8; ++i) o[c8 * 8 + i] = t8[i];
+        }
+      }
+    };
+
+    for (int clip = blockIdx.x; clip < P.B; clip += gridDim.x) {
+      float* xc = P.x + (long long)clip * J * T;
+      const float* zc = P.z + (long long)clip * J * T;
+      const float* condc = P.cond + (long long)clip * T * D;
+      for (int k = 0; k < P.n_run; ++k) {
+        const int index = first_index - k;
+        const int trow = P.tmap[index];
+        const bool nz = (index != 0) && (P.sampler == 0);
+        // ---------------- stage the A operand of the input GEMM: x_t [J][T] fp32 -> bf16 k-blocks [frame+1][64 channels]
+        ph.wait(bars, B_BUFF + 0); ph.wait(bars, B_BUFF + 1);
+        for (int kb = 0; kb < JPAD / 64; ++kb) {
+          const int sl = kb & 3;
+          ph.wait(bars, B_AEMPTY + sl);
+          uint8_t* at = BUF + sl * KT;
+          float lo[11], hi[11];
+#pragma unroll
+          for (int m = 0; m < 11; ++m) {
+            const int it = wt + 256 * m;                 // 0..2815 = 32 channel pairs x 88 frames
+            const int pr = it / T, f = it - pr * T;
+            const int j = kb * 64 + 2 * pr;
+            lo[m] = (j < J) ? xc[(long long)j * T + f] : 0.f;      // plain loads: x is rewritten by this CTA every step
+            hi[m] = (j + 1 < J) ? xc[(long long)(j + 1) * T + f] : 0.f;
+          }
+#pragma unroll
+          for (int m = 0; m < 11; ++m) {
+            const int it = wt + 256 * m;
+            const int pr = it / T, f = it - pr * T;
+            const int rr = f + 1, cc = 2 * pr;
+            *reinterpret_cast<uint32_t*>(at + (rr >> 3) * 1024 + (rr & 7) * 128 + (((cc >> 3) ^ (rr & 7)) << 4) + (cc & 7) * 2) =
+                pack_bf16x2(lo[m], hi[m]);
+          }
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bars[B_AFULL + sl]);
+        }
+        lap(PF_W_STAGE);
+        // ---------------- input epilogue: + cond + TW[t], rotary (position = frame), bf16 -> Z staging (in BUF)
+        ph.wait(bars, B_ACCR + 0); ph.wait(bars, B_ACCR + 1);
+        lap(PF_W_IN_WAIT);
+        tcgen05_fence_after();
+        {
+          const int f = r - 1;
+          const bool ok = r >= 1 && r <= T;
+#pragma unroll 1
+          for (int c4 = 0; c4 < 4; ++c4) {
+            const int col0 = sub * 128 + c4 * 32;      // == local head (sub*4 + c4) * 32
+            tmem_ld32(tlane + col0, v);
+            if (!ok) continue;
+            const float* cr = condc + (long long)f * D + col0;
+            const float* tw = P.TW + (long long)trow * D + col0;
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              const float4 c = __ldg(reinterpret_cast<const float4*>(cr + i));
+              const float4 t4 = __ldg(reinterpret_cast<const float4*>(tw + i));
+              v[i] += c.x + t4.x; v[i + 1] += c.y + t4.y; v[i + 2] += c.z + t4.z; v[i + 3] += c.w + t4.w;
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float2 cs = __ldg(P.cs + f * 16 + i);
+              const float a = v[i], b = v[i + 16];
+              v[i] = a * cs.x - b * cs.y;
+              v[i + 16] = b * cs.x + a * cs.y;
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(Zs + f * ZLD + col0 + i * 8) = pack8(v + i * 8);
+          }
+        }
+        release_acc(0, 1, false, -1);
+        workers_sync();
+        lap(PF_W_IN_EPI);
+        // ---------------- windowed causal local attention on mma.sync (q = k = v = Z), rotary (position = frame + 1) -> XS
+        for (int item = ww; item < 64; item += 8) {
+          const int w = item >> 3, lh = item & 7;
+          const int q0 = WIN * w, k0 = (w == 0) ? 0 : WIN * (w - 1), nk = q0 + WIN - k0;
+          float sc[4][4];
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt) { sc[nt][0] = sc[nt][1] = sc[nt][2] = sc[nt][3] = 0.f; }
+#pragma unroll
+          for (int kk = 0; kk < 2; ++kk) {
+            uint32_t a[4], b0, b1, b2, b3, c0, c1;
+            ldsm_x4(a[0], a[1], a[2], a[3], Zs + (q0 + (lane & 7) + ((lane >> 3) & 1) * 8) * ZLD + lh * 32 + kk * 16 + (lane >> 4) * 8);
+            ldsm_x4(b0, b1, b2, b3, Zs + (k0 + (lane & 7) + (lane >> 4) * 8) * ZLD + lh * 32 + kk * 16 + ((lane >> 3) & 1) * 8);
+            ldsm_x2(c0, c1, Zs + (k0 + 16 + (lane & 7)) * ZLD + lh * 32 + kk * 16 + ((lane >> 3) & 1) * 8);
+            mma_bf16_16816(sc[0], a, b0, b1);
+            mma_bf16_16816(sc[1], a, b2, b3);
+            mma_bf16_16816(sc[2], a, c0, c1);
+          }
+          const int g = lane >> 2, t2 = (lane & 3) * 2;
+          float mx0 = -3.0e38f, mx1 = -3.0e38f;
+#pragma unroll
+          for (int nt = 0; nt < 3; ++nt)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int cc = nt * 8 + t2 + e;
+              if (!(cc < nk && k0 + cc <= q0 + g)) sc[nt][e] = -3.0e38f;
+              if (!(cc < nk && k0 + cc <= q0 + g + 8)) sc[nt][2 + e] = -3.0e38f;
+              mx0 = fmaxf(mx0, sc[nt][e]); mx1 = fmaxf(mx1, sc[nt][2 + e]);
+            }
+          mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+          mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+          const float sl2 = 1.4426950408889634f * 0.17677669529663687f;     // log2(e) / sqrt(32)
+          float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+          for (int nt = 0; nt < 3; ++nt) {
+            sc[nt][0] = exp2f((sc[nt][0] - mx0) * sl2); sc[nt][1] = exp2f((sc[nt][1] - mx0) * sl2);
+            sc[nt][2] = exp2f((sc[nt][2] - mx1) * sl2); sc[nt][3] = exp2f((sc[nt][3] - mx1) * sl2);
+            s0 += sc[nt][0] + sc[nt][1]; s1 += sc[nt][2] + sc[nt][3];
+          }
+          s0 += __shfl_xor_sync(0xffffffffu, s0, 1); s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
+          s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+          float oc[4][4];
+#pragma unroll
+          for (int dt = 0; dt < 4; ++dt) { oc[dt][0] = oc[dt][1] = oc[dt][2] = oc[dt][3] = 0.f; }
+#pragma unroll
+          for (int kt = 0; kt < 2; ++kt) {
+            uint32_t a[4];
+            a[0] = pack_bf16x2(sc[2 * kt][0], sc[2 * kt][1]); a[1] = pack_bf16x2(sc[2 * kt][2], sc[2 * kt][3]);
+            a[2] = pack_bf16x2(sc[2 * kt + 1][0], sc[2 * kt + 1][1]); a[3] = pack_bf16x2(sc[2 * kt + 1][2], sc[2 * kt + 1][3]);
+#pragma unroll
+            for (int dp = 0; dp < 2; ++dp) {
+              uint32_t b0, b1, b2, b3;
+              ldsm_x4_t(b0, b1, b2, b3, Zs + (k0 + kt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * ZLD + lh * 32 + dp * 16 + (lane >> 4) * 8);
+              mma_bf16_16816(oc[2 * dp], a, b0, b1);
+              mma_bf16_16816(oc[2 * dp + 1], a, b2, b3);
+            }
+          }
+          const float i0 = 1.0f / s0, i1 = 1.0f / s1;
+#pragma unroll
+          for (int hr = 0; hr < 2; ++hr) {
+            const int rr = g + 8 * hr;
+            if (rr >= WIN) continue;
+            const int pos = q0 + rr + 1;                 // XS row (token is row 0) == rotary position
+            const float inv = hr ? i1 : i0;
+#pragma unroll
+            for (int dt = 0; dt < 2; ++dt) {
+              float ol[2], oh[2];
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                const float2 cs = __ldg(P.cs + pos * 16 + dt * 8 + t2 + e);
+                const float a = oc[dt][2 * hr + e] * inv, b = oc[dt + 2][2 * hr + e] * inv;
+                ol[e] = a * cs.x - b * cs.y;
+                oh[e] = b * cs.x + a * cs.y;
+              }
+              *reinterpret_cast<uint32_t*>(XS + a_off(pos, lh * 32 + dt * 8 + t2)) = pack_bf16x2(ol[0], ol[1]);
+              *reinterpret_cast<uint32_t*>(XS + a_off(pos, lh * 32 + 16 + dt * 8 + t2)) = pack_bf16x2(oh[0], oh[1]);
+            }
+          }
+        }
+        {   // token row: tok = emb_1 + emb_t (rotary at position 0 is the identity)
+          const float tv = __ldg(P.emb1 + (long long)clip * D + wt) + __ldg(P.te + (long long)trow * D + wt);
+          *reinterpret_cast<__nv_bfloat16*>(XS + a_off(0, wt)) = __float2bfloat16_rn(tv);
+        }
+        fence_async_smem();
+        workers_sync();                                  // Z staging (BUF) is dead from here on
+        if (lane == 0) mbar_arrive(&bars[B_XSR]);
+        lap(PF_W_LOCAL);
+        debug_dump(0, clip);
+
+        // ---------------- transformer layers
+        for (int l = 0; l < NL; ++l) {
+          const float* lp = P.lparams + (long long)l * P_SIZE;
+          for (int h = 0; h < NH; ++h) {
+            const int hb = h & 1;
+            ph.wait(bars, B_ACCR + 2 * hb); ph.wait(bars, B_ACCR + 2 * hb + 1);
+            lap(PF_W_QKV_WAIT);
+            tcgen05_fence_after();
+            // q | k | v of this head: 6 chunks of 32 columns; column-half 0 takes q0 q1 k0, half 1 takes k1 v0 v1
+#pragma unroll 1
+            for (int ci = 0; ci < 3; ++ci) {
+              const int ch = sub * 3 + ci;               // 0..5
+              tmem_ld32(tlane + hb * 256 + ch * 32, v);
+              if (r >= 96) continue;
+              __nv_bfloat16* dst = (ch < 2 ? Qs : (ch < 4 ? Ks : Vs)) + r * QLD + (ch & 1) * 32;
+              if (r < S) {
+                const float* bq = lp + P_BQKV + h * 192 + ch * 32;
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                  const float4 b4 = __ldg(reinterpret_cast<const float4*>(bq + i));
+                  v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(dst + i * 8) = pack8(v + i * 8);
+              } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(dst + i * 8) = make_uint4(0u, 0u, 0u, 0u);
+              }
+            }
+            release_acc(2 * hb, 2 * hb + 1, false, -1);
+            if (l > 0 && hb == 0) ph.wait(bars, B_BUFF + (h >> 1));    // linear2 of the previous layer has consumed this BUF half
+            workers_sync();
+            if (ww * 16 < S) {
+              // ---- softmax(q k^T / 8) v for query rows 16*ww .. +15 (FlashAttention-2 register reuse)
+              const int r0 = ww * 16;
+              float sc[12][4];
+#pragma unroll
+              for (int nt = 0; nt < 12; ++nt) { sc[nt][0] = sc[nt][1] = sc[nt][2] = sc[nt][3] = 0.f; }
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk) {
+                uint32_t a[4];
+                ldsm_x4(a[0], a[1], a[2], a[3], Qs + (r0 + (lane & 7) + ((lane >> 3) & 1) * 8) * QLD + kk * 16 + (lane >> 4) * 8);
+#pragma unroll
+                for (int np = 0; np < 6; ++np) {
+                  uint32_t b0, b1, b2, b3;
+                  ldsm_x4(b0, b1, b2, b3, Ks + (np * 16 + (lane & 7) + (lane >> 4) * 8) * QLD + kk * 16 + ((lane >> 3) & 1) * 8);
+                  mma_bf16_16816(sc[2 * np], a, b0, b1);
+                  mma_bf16_16816(sc[2 * np + 1], a, b2, b3);
+                }
+              }
+              const int cbase = (lane & 3) * 2;
+              float mx0 = -3.0e38f, mx1 = -3.0e38f;
+#pragma unroll
+              for (int nt = 0; nt < 12; ++nt) {
+                const int c = nt * 8 + cbase;
+                if (c >= S) { sc[nt][0] = -3.0e38f; sc[nt][2] = -3.0e38f; }
+                if (c + 1 >= S) { sc[nt][1] = -3.0e38f; sc[nt][3] = -3.0e38f; }
+                mx0 = fmaxf(mx0, fmaxf(sc[nt][0], sc[nt][1]));
+                mx1 = fmaxf(mx1, fmaxf(sc[nt][2], sc[nt][3]));
+              }
+              mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+              mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+              const float sl2 = 1.4426950408889634f * 0.125f;
+              float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+              for (int nt = 0; nt < 12; ++nt) {
+                sc[nt][0] = exp2f((sc[nt][0] - mx0) * sl2); sc[nt][1] = exp2f((sc[nt][1] - mx0) * sl2);
+                sc[nt][2] = exp2f((sc[nt][2] - mx1) * sl2); sc[nt][3] = exp2f((sc[nt][3] - mx1) * sl2);
+                s0 += sc[nt][0] + sc[nt][1]; s1 += sc[nt][2] + sc[nt][3];
+              }
+              s0 += __shfl_xor_sync(0xffffffffu, s0, 1); s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
+              s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+              float oc[8][4];
+#pragma unroll
+              for (int dt = 0; dt < 8; ++dt) { oc[dt][0] = oc[dt][1] = oc[dt][2] = oc[dt][3] = 0.f; }
+#pragma unroll
+              for (int kt = 0; kt < 6; ++kt) {
+                uint32_t a[4];
+                a[0] = pack_bf16x2(sc[2 * kt][0], sc[2 * kt][1]); a[1] = pack_bf16x2(sc[2 * kt][2], sc[2 * kt][3]);
+                a[2] = pack_bf16x2(sc[2 * kt + 1][0], sc[2 * kt + 1][1]); a[3] = pack_bf16x2(sc[2 * kt + 1][2], sc[2 * kt + 1][3]);
+#pragma unroll
+                for (int dp = 0; dp < 4; ++dp) {
+                  uint32_t b0, b1, b2, b3;
+                  ldsm_x4_t(b0, b1, b2, b3, Vs + (kt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * QLD + dp * 16 + (lane >> 4) * 8);
+                  mma_bf16_16816(oc[2 * dp], a, b0, b1);
+                  mma_bf16_16816(oc[2 * dp + 1], a, b2, b3);
+                }
+              }
+              const float i0 = 1.0f / s0, i1 = 1.0f / s1;
+              const int row0 = r0 + (lane >> 2), row1 = row0 + 8;
+#pragma unroll
+              for (int dt = 0; dt < 8; ++dt) {
+                const int c = h * HD + dt * 8 + cbase;
+                *reinterpret_cast<uint32_t*>(BUF + a_off(row0, c)) = pack_bf16x2(oc[dt][0] * i0, oc[dt][1] * i0);
+                *reinterpret_cast<uint32_t*>(BUF + a_off(row1, c)) = pack_bf16x2(oc[dt][2] * i1, oc[dt][3] * i1);
+              }
+            }
+            fence_async_smem();
+            workers_sync();                              // staging may be overwritten; this head's k-tile of BUF is complete
+            if (hb == 1 && lane == 0) mbar_arrive(&bars[B_BUFR + (h >> 1)]);
+            lap(PF_W_ATT);
+          }
+          layernorm_epilogue(lp + P_BO, lp + P_G1, lp + P_BE1);
+          // ---- FFN: GELU epilogue per 128-unit chunk -> BUF half (c & 1) as the A operand of linear2
+          for (int c = 0; c < 8; ++c) {
+            const int qd = 2 + (c & 1);
+            ph.wait(bars, B_ACCR + qd);
+            ph.wait(bars, B_BUFF + (c & 1));
+            lap(PF_W_GELU_WAIT);
+            tcgen05_fence_after();
+#pragma unroll 1
+            for (int ci = 0; ci < 2; ++ci) {
+              const int cc0 = sub * 64 + ci * 32;        // column inside the chunk
+              tmem_ld32(tlane + qd * 128 + cc0, v);
+              const float* b1 = lp + P_B1 + c * 128 + cc0;
+#pragma unroll
+              for (int i = 0; i < 32; i += 4) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(b1 + i));
+                v[i] = gelu_fast(v[i] + b4.x); v[i + 1] = gelu_fast(v[i + 1] + b4.y);
+                v[i + 2] = gelu_fast(v[i + 2] + b4.z); v[i + 3] = gelu_fast(v[i + 3] + b4.w);
+              }
+#pragma unroll
+              for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(BUF + a_off(r, (c & 1) * 128 + cc0 + i * 8)) = pack8(v + i * 8);
+            }
+            release_acc(qd, -1, false, c & 1);
+            lap(PF_W_GELU);
+          }
+          layernorm_epilogue(lp + P_B2, lp + P_G2, lp + P_BE2);
+          debug_dump(l + 1, clip);
+        }
+
+        // ---------------- pose head + posterior: x <- f(x0, x, z) in place, coalesced along frames
+        if (nz) ph.wait(bars, B_ZR);
+        lap(PF_W_ZWAIT);
+        {
+          const float4 cf = P.coef[index];
+          const int f = r - 1;
+          const bool ok = r >= 1 && r <= T;
+          for (int t = 0; t < JPAD / 128; ++t) {
+            ph.wait(bars, B_ACCR + (t & 3));
+            lap(PF_W_HEAD_WAIT);
+            tcgen05_fence_after();
+#pragma unroll 1
+            for (int ci = 0; ci < 2; ++ci) {
+              const int j0 = t * 128 + sub * 64 + ci * 32;
+              tmem_ld32(tlane + (t & 3) * 128 + sub * 64 + ci * 32, v);
+              if (!ok || j0 >= J) continue;
+              const long long base = (long long)j0 * T + f;
+              float xt[32], zz[32];
+#pragma unroll
+              for (int i = 0; i < 32; ++i) xt[i] = (j0 + i < J) ? xc[base + (long long)i * T] : 0.f;
+#pragma unroll
+              for (int i = 0; i < 32; ++i) zz[i] = (nz && j0 + i < J) ? zc[base + (long long)i * T] : 0.f;
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                const float x0 = v[i] + __ldg(P.bout + j0 + i);
+                v[i] = posterior_apply(P.sampler, cf, x0, xt[i], zz[i], nz);
+              }
+#pragma unroll
+              for (int i = 0; i < 32; ++i) if (j0 + i < J) xc[base + (long long)i * T] = v[i];
+            }
+            release_acc(t & 3, -1, false, -1);
+            lap(PF_W_HEAD);
+          }
+        }
+        __syncwarp();
+        if (nz && lane == 0) mbar_arrive(&bars[B_ZF]);
+        workers_sync();                                  // x_{t-1} of every frame is visible to the staging loop of the next step
+      }
+    }
+    if (prof) for (int i = PF_W_STAGE; i < PF_COUNT; ++i) P.prof[i] = pf[i];
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+  }
+}
+
+}  // namespace clip

@@ -636,6 +636,14 @@ extern "C" int64_t dsg_debug_read(dsg_engine* e, const char* name, int32_t B, fl
     return 0;
   }
   if (!dst) return dsg_fail(DSG_ERR_BAD_SHAPE, "null dst");
+  if (!strcmp(name, "clipprof")) {      // cycle counters of the clip kernel (DSG_CLIP_PROF=1), returned as floats
+    if (!dsg_tc_clip_prof(e) || capacity < 32) return dsg_fail(DSG_ERR_STATE, "no clip-kernel profile");
+    CUDA_TRY(cudaDeviceSynchronize());
+    long long h[32];
+    CUDA_TRY(cudaMemcpy(h, dsg_tc_clip_prof(e), sizeof h, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < 32; ++i) dst[i] = (float)h[i];
+    return 32;
+  }
   if (B <= 0 || B > e->d.max_batch) return dsg_fail(DSG_ERR_BAD_SHAPE, "batch");
   CUDA_TRY(cudaDeviceSynchronize());
   if (!strcmp(name, "h_in")) {

@@ -110,5 +110,6 @@ int dsg_run_steps(dsg_engine* e, int B, float* xd, int n_run, int first_index, u
 int dsg_tc_create(dsg_engine* e);
 void dsg_tc_destroy(dsg_engine* e);
 const float* dsg_tc_h(dsg_engine* e);
+const long long* dsg_tc_clip_prof(dsg_engine* e);
 int dsg_tc_denoise(dsg_engine* e, int B, const float* x, const int* tsel, StepRef step, float* out, cudaStream_t st);
 int dsg_tc_run_steps(dsg_engine* e, int B, float* xd, int n_run, int first_index, uint64_t seed, int segment, cudaStream_t st);

@@ -15,6 +15,7 @@
 #include "dsg_engine.h"
 #include "dsg_tc_gemm.cuh"
 #include "dsg_tc_kernels.cuh"
+#include "dsg_clip_kernel.cuh"
 
 using bf16 = __nv_bfloat16;
 using namespace tc;
@@ -33,6 +34,12 @@ struct dsg_tc_state {
   cudaGraphExec_t exec = nullptr;
   int graph_B = 0, graph_sampler = -1;
   int nodes_per_step = 0;
+  // clip kernel (one persistent CTA per clip): weight slabs + parameter blocks
+  bool clip_ok = false;
+  bf16 *wK256 = nullptr, *wK1024 = nullptr;
+  float *lparams = nullptr, *bout = nullptr;
+  long long* prof = nullptr;
+  CUtensorMap tm_cin, tm_c128, tm_c64, tm_cw2;
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -96,6 +103,69 @@ static int pack_w(const float* src, bf16* dst, int rows, int cols, long long ld,
 }
 
 // ---------------------------------------------------------------------------------------------------
+// clip kernel set-up: weight slabs in the row order clip::R_* expects, fp32 parameter blocks, tensor maps
+static int clip_setup(dsg_engine* e) {
+  dsg_tc_state* t = e->tc;
+  const dsg_model_desc& d = e->d;
+  using namespace clip;
+  if (d.variant != DSG_VARIANT_ATTN3 && d.variant != DSG_VARIANT_ATTN4) return DSG_OK;
+  if (d.njoints != J || d.n_poses != T || d.latent_dim != D || d.ff_size != F || d.num_layers != NL || d.num_heads != NH ||
+      d.local_heads != LH || d.local_window != WIN) return DSG_OK;           // other geometries run on the multi-kernel path
+  const size_t rows256 = (size_t)R_HEAD + JPAD;
+  TRY(dalloc0(&t->wK256, rows256 * D));
+  TRY(dalloc0(&t->wK1024, (size_t)NL * D * F));
+  std::vector<float> lp((size_t)NL * P_SIZE, 0.f), tmp(4096);
+  auto fetch = [&](const float* dev, float* dst, size_t n) { return cudaMemcpy(dst, dev, n * sizeof(float), cudaMemcpyDeviceToHost); };
+  for (int l = 0; l < NL; ++l) {
+    float* const* w = &e->w[W_LAYER0 + 12 * l];
+    bf16* base = t->wK256 + (size_t)l * R_LAYER * D;
+    for (int h = 0; h < NH; ++h)
+      for (int part = 0; part < 3; ++part)
+        TRY(pack_w(w[L_INPROJ_W] + (size_t)(part * D + h * HD) * D, base + (size_t)(R_QKV + h * 192 + part * 64) * D, 64, D, D, 64, D));
+    TRY(pack_w(w[L_OUTPROJ_W], base + (size_t)R_WO * D, D, D, D, D, D));
+    TRY(pack_w(w[L_FF1_W], base + (size_t)R_W1 * D, F, D, D, F, D));
+    TRY(pack_w(w[L_FF2_W], t->wK1024 + (size_t)l * D * F, D, F, F, D, F));
+    float* p = lp.data() + (size_t)l * P_SIZE;
+    CUDA_TRY(fetch(w[L_INPROJ_B], tmp.data(), 3 * D));
+    for (int h = 0; h < NH; ++h)
+      for (int part = 0; part < 3; ++part)
+        for (int i = 0; i < 64; ++i) p[P_BQKV + h * 192 + part * 64 + i] = tmp[part * D + h * HD + i];
+    CUDA_TRY(fetch(w[L_OUTPROJ_B], p + P_BO, D)); CUDA_TRY(fetch(w[L_N1_W], p + P_G1, D)); CUDA_TRY(fetch(w[L_N1_B], p + P_BE1, D));
+    CUDA_TRY(fetch(w[L_FF1_B], p + P_B1, F));    CUDA_TRY(fetch(w[L_FF2_B], p + P_B2, D));
+    CUDA_TRY(fetch(w[L_N2_W], p + P_G2, D));     CUDA_TRY(fetch(w[L_N2_B], p + P_BE2, D));
+  }
+  TRY(pack_w(e->w[W_OUT_W], t->wK256 + (size_t)R_HEAD * D, J, D, D, JPAD, D));
+  TRY(dalloc0(&t->lparams, lp.size()));
+  CUDA_TRY(cudaMemcpy(t->lparams, lp.data(), lp.size() * sizeof(float), cudaMemcpyHostToDevice));
+  TRY(dalloc0(&t->bout, (size_t)JPAD));
+  TRY(dalloc0(&t->prof, (size_t)64));
+  CUDA_TRY(cudaMemcpy(t->bout, e->w[W_OUT_B], (size_t)J * sizeof(float), cudaMemcpyDeviceToDevice));
+  TRY(make_tmap(&t->tm_cin, t->Wxp, D, JPAD, 128));
+  TRY(make_tmap(&t->tm_c128, t->wK256, rows256, D, 128));
+  TRY(make_tmap(&t->tm_c64, t->wK256, rows256, D, 64));
+  TRY(make_tmap(&t->tm_cw2, t->wK1024, (uint64_t)NL * D, F, 128));
+  CUDA_TRY(cudaFuncSetAttribute(clip::clip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  t->clip_ok = true;
+  return DSG_OK;
+}
+
+static int clip_run(dsg_engine* e, int B, float* xd, int n_run, int first_index, uint64_t seed, int segment, cudaStream_t st) {
+  dsg_tc_state* t = e->tc;
+  TRY(dsg_upload_loop_params(e, first_index, seed, segment, st));
+  clip::ClipParams p;
+  p.x = xd; p.z = t->z; p.cond = e->cond; p.emb1 = e->emb1; p.te = e->te; p.TW = e->TW; p.cs = e->cs_local;
+  p.lparams = t->lparams; p.bout = t->bout; p.coef = e->coef; p.tmap = e->tmap; p.clip_ids = e->clip_ids; p.lp = e->d_loop;
+  p.B = B; p.n_run = n_run; p.sampler = e->sampler;
+  p.prof = getenv("DSG_CLIP_PROF") ? t->prof : nullptr;
+  p.dbg = e->dbg; p.dbg_slot = (long long)e->d.max_batch * e->S * e->d.latent_dim; p.debug = e->debug ? 1 : 0;
+  const int grid = B < e->num_sms ? B : e->num_sms;
+  clip::clip_kernel<<<grid, 384, clip::SMEM_BYTES, st>>>(t->tm_cin, t->tm_c128, t->tm_c64, t->tm_cw2, p);
+  e->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return DSG_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
 int dsg_tc_create(dsg_engine* e) {
   const dsg_model_desc& d = e->d;
   if (d.latent_dim != 256)
@@ -145,16 +215,18 @@ int dsg_tc_create(dsg_engine* e) {
   CUDA_TRY(cudaEventCreateWithFlags(&t->ev_join, cudaEventDisableTiming));
   CUDA_TRY(cudaEventCreateWithFlags(&t->ev_in, cudaEventDisableTiming));
   CUDA_TRY(cudaEventCreateWithFlags(&t->ev_out, cudaEventDisableTiming));
+  TRY(clip_setup(e));
   return DSG_OK;
 }
 
 const float* dsg_tc_h(dsg_engine* e) { return e->tc ? e->tc->hS : nullptr; }
+const long long* dsg_tc_clip_prof(dsg_engine* e) { return e->tc ? e->tc->prof : nullptr; }
 
 void dsg_tc_destroy(dsg_engine* e) {
   dsg_tc_state* t = e->tc;
   if (!t) return;
   if (t->exec) cudaGraphExecDestroy(t->exec);
-  void* ptrs[] = {t->Wxp, t->Wout, t->xb, t->xsb, t->qkvb, t->attb, t->ffb, t->hS, t->z, t->xloop};
+  void* ptrs[] = {t->Wxp, t->Wout, t->xb, t->xsb, t->qkvb, t->attb, t->ffb, t->hS, t->z, t->xloop, t->wK256, t->wK1024, t->lparams, t->bout, t->prof};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (auto& v : {t->Wqkv, t->Wo, t->W1, t->W2}) for (bf16* p : v) if (p) cudaFree(p);
   if (t->main) cudaStreamDestroy(t->main);
@@ -303,6 +375,9 @@ static int tc_capture(dsg_engine* e, int B) {
 
 int dsg_tc_run_steps(dsg_engine* e, int B, float* xd, int n_run, int first_index, uint64_t seed, int segment, cudaStream_t st) {
   dsg_tc_state* t = e->tc;
+  // DSG_TC_MODE=kernels selects the multi-kernel graph path (default: the persistent clip kernel when the geometry allows)
+  const bool force_kernels = getenv("DSG_TC_MODE") && !strcmp(getenv("DSG_TC_MODE"), "kernels");
+  if (t->clip_ok && !force_kernels && !e->profiling) return clip_run(e, B, xd, n_run, first_index, seed, segment, st);
   if (e->profiling || e->debug) {
     TRY(tc_pack_x(e, B, xd, st));
     for (int k = 0; k < n_run; ++k) {

@@ -132,3 +132,47 @@ def test_full_clip_1000_steps_bf16_bvh_vs_reference_golden(gold_dir, sd):
     print(f"bf16 full clip: poses max err {np.abs(poses - gold['poses']).max():.3g}; BVH positions {d_pos:.3g} cm; "
           f"Euler max {d_eul.max():.3g} deg, mean {d_eul.mean():.3g} deg")
     assert d_pos < 0.4 and d_eul.max() < 1.0
+
+
+def test_clip_kernel_matches_multikernel_path(sd):
+    """The persistent per-clip kernel (default) against the multi-kernel graph path (DSG_TC_MODE=kernels): same bf16
+    GEMM operands; the clip kernel additionally keeps the residual stream in bf16 on chip.  Per-layer taps of the last
+    step and the final sample are compared; 148+ clips also exercises CTAs that run more than one clip."""
+    d = create_gaussian_diffusion([6])
+    B = 3
+    y = synthetic_conditioning(G, B, segment=0)
+    shp = (B, G.njoints, 1, G.n_poses)
+    res = {}
+    for mode in ("kernels", "clip"):
+        os.environ["DSG_TC_MODE"] = mode
+        eng_model = _model(sd, max_batch=B)
+        eng = eng_model.get_engine(B)
+        eng.debug_enable()
+        out = d.p_sample_loop(eng_model, shp, clip_denoised=False, model_kwargs={'y': dict(y, noise_seed=SEED, segment=0)})
+        res[mode] = (out.cpu(), {k: eng.debug_read(k, B) for k in ("xs0", "xs1", "xs4", "xs8")})
+    os.environ.pop("DSG_TC_MODE")
+    for k in ("xs0", "xs1", "xs4", "xs8"):
+        mx, rms = _err(res["clip"][1][k], res["kernels"][1][k])
+        print(f"clip vs kernels tap {k}: max {mx:.3g} rms {rms:.3g}")
+        assert mx < 0.08 and rms < 0.01, k
+    mx, rms = _err(res["clip"][0], res["kernels"][0])
+    print(f"clip vs kernels final sample: max {mx:.3g} rms {rms:.3g}")
+    assert mx < 0.05 and rms < 0.008
+    want, _ = O.p_sample_loop(sd, G, O.Schedule(1000, [6]), y, B, seed=SEED, segment=0)
+    mx, rms = _err(res["clip"][0], want)
+    print(f"clip vs oracle final sample: max {mx:.3g} rms {rms:.3g}")
+    assert mx < 0.05 and rms < 0.008
+
+
+def test_clip_kernel_many_clips_per_cta(sd):
+    """More clips than SMs: CTAs loop over several clips; results must equal a run where every clip has its own CTA."""
+    d = create_gaussian_diffusion([3])
+    B = 150
+    y = synthetic_conditioning(G, B, segment=0)
+    m = _model(sd, max_batch=B)
+    full = d.p_sample_loop(m, (B, G.njoints, 1, G.n_poses), clip_denoised=False,
+                           model_kwargs={'y': dict(y, noise_seed=SEED, segment=0, clip_ids=list(range(B)))})
+    ys = {k: (v[147:150] if isinstance(v, torch.Tensor) and v.shape[0] == B else v) for k, v in y.items()}
+    part = d.p_sample_loop(m, (3, G.njoints, 1, G.n_poses), clip_denoised=False,
+                           model_kwargs={'y': dict(ys, noise_seed=SEED, segment=0, clip_ids=[147, 148, 149])})
+    assert _err(part, full[147:150])[0] < 1e-5
