@@ -32,7 +32,8 @@ constexpr int OFF_Q = OFF_W + NS * WSTAGE;
 constexpr int OFF_K = OFF_Q + 96 * QLD * 2;
 constexpr int OFF_V = OFF_K + 96 * QLD * 2;
 constexpr int OFF_RED = OFF_V + 96 * QLD * 2;
-constexpr int OFF_BAR = OFF_RED + 2048;
+constexpr int OFF_B1 = OFF_RED + 2048;           // per-layer parameters staged in shared memory (fp32): b1[1024] | bq[256] | bo'[256] | b2[256]
+constexpr int OFF_BAR = OFF_B1 + 4096 + 3072;
 constexpr int SMEM_BYTES = OFF_BAR + 512 + 1024;
 constexpr int ZLD = 264;                    // rope'd h staging row stride (bf16), lives in BUF: 104 rows x 528 B
 constexpr int ZROWS = 104;
@@ -95,12 +96,22 @@ DSG_DEVINL void unpack8(const uint4 u, float* v) {
 enum { PF_TOTAL = 0, PF_MMA_WAIT_W, PF_MMA_WAIT_OTHER, PF_PROD_WAIT_EMPTY, PF_W_STAGE, PF_W_IN_WAIT, PF_W_IN_EPI, PF_W_LOCAL,
        PF_W_QKV_WAIT, PF_W_ATT, PF_W_LN_WAIT, PF_W_LN, PF_W_GELU_WAIT, PF_W_GELU, PF_W_HEAD_WAIT, PF_W_HEAD, PF_W_ZWAIT, PF_COUNT };
 
+// consumers of tcgen05.ld results must not be scheduled above tcgen05.wait::ld: pass the registers through an empty
+// volatile asm placed after the wait
+DSG_DEVINL void tie32(float* v) {
+  asm volatile("" : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7]), "+f"(v[8]), "+f"(v[9]),
+               "+f"(v[10]), "+f"(v[11]), "+f"(v[12]), "+f"(v[13]), "+f"(v[14]), "+f"(v[15]), "+f"(v[16]), "+f"(v[17]), "+f"(v[18]),
+               "+f"(v[19]), "+f"(v[20]), "+f"(v[21]), "+f"(v[22]), "+f"(v[23]), "+f"(v[24]), "+f"(v[25]), "+f"(v[26]), "+f"(v[27]),
+               "+f"(v[28]), "+f"(v[29]), "+f"(v[30]), "+f"(v[31]) :: "memory");
+}
+
 struct Phases {            // one phase bit per barrier, toggled on every completed wait
   uint32_t bits;
   DSG_DEVINL void wait(uint64_t* bars, int id) { mbar_wait(&bars[id], (bits >> id) & 1u); bits ^= 1u << id; }
 };
 
 // ---------------------------------------------------------------------------------------------------
+template <bool PROF>
 __global__ void __launch_bounds__(384, 1)
 clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152]   box 128 x 64
             const __grid_constant__ CUtensorMap tm_w128,   // K=256 slab          box 128 x 64
@@ -150,7 +161,7 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
       Phases ph{0x7u << B_WEMPTY};                 // "empty" barriers start free
       int slot = 0;
       long long t_wait = 0;
-      const bool prof = P.prof != nullptr && blockIdx.x == 0;
+      const bool prof = PROF && P.prof != nullptr && blockIdx.x == 0;
       auto load = [&](const CUtensorMap* m, int row, int kcol, uint32_t bytes) {
         const long long c0 = prof ? clock64() : 0;
         ph.wait(bars, B_WEMPTY + slot);
@@ -192,7 +203,7 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
       constexpr uint32_t idesc128 = make_idesc_bf16(128, 128), idesc64 = make_idesc_bf16(128, 64);
       // one weight tile: 4 UMMAs (K = 64) of A k-tile `a_tile` against the current stage
       long long t_w = 0, t_o = 0;
-      const bool prof = P.prof != nullptr && blockIdx.x == 0;
+      const bool prof = PROF && P.prof != nullptr && blockIdx.x == 0;
       const long long t_begin = clock64();
       auto tile = [&](uint32_t a_tile, uint32_t d_col, uint32_t idesc, bool acc_first) {
         const long long c0 = prof ? clock64() : 0;
@@ -301,19 +312,20 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
     __nv_bfloat16* Ks = reinterpret_cast<__nv_bfloat16*>(smem + OFF_K);
     __nv_bfloat16* Vs = reinterpret_cast<__nv_bfloat16*>(smem + OFF_V);
     float* red = reinterpret_cast<float*>(smem + OFF_RED);
+    float* b1s = reinterpret_cast<float*>(smem + OFF_B1);
     uint8_t* XS = smem + OFF_XS;
     uint8_t* BUF = smem + OFF_BUF;
     float v[32];
-    const bool prof = P.prof != nullptr && blockIdx.x == 0 && wt == 0;
-    long long pf[PF_COUNT];
+    const bool prof = PROF && P.prof != nullptr && blockIdx.x == 0 && wt == 0;
+    long long pf[PROF ? PF_COUNT : 1];
 #pragma unroll
-    for (int i = 0; i < PF_COUNT; ++i) pf[i] = 0;
-    long long tmark = clock64();
-    auto lap = [&](int id) { if (prof) { const long long c = clock64(); pf[id] += c - tmark; tmark = c; } };
+    for (int i = 0; i < (PROF ? PF_COUNT : 1); ++i) pf[i] = 0;
+    long long tmark = PROF ? clock64() : 0;
+    auto lap = [&](int id) { if constexpr (PROF) { if (prof) { const long long c = clock64(); pf[id] += c - tmark; tmark = c; } } };
 
     auto release_acc = [&](int qa, int qb, bool xs_ready, int buf_ready) {
       tcgen05_fence_before();
-      fence_async_smem();
+      if (xs_ready || buf_ready >= 0) fence_async_smem();
       __syncwarp();
       if (lane == 0) {
         mbar_arrive(&bars[B_ACCF + qa]);
@@ -336,8 +348,8 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
         for (int i = 0; i < 4; ++i) {
           float rs[8];
           unpack8(*reinterpret_cast<const uint4*>(XS + a_off(r, col0 + i * 8)), rs);
-          const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + col0 + i * 8));
-          const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + col0 + i * 8 + 4));
+          const float4 b0 = *reinterpret_cast<const float4*>(bias + col0 + i * 8);        // shared memory (staged per layer)
+          const float4 b1 = *reinterpret_cast<const float4*>(bias + col0 + i * 8 + 4);
           v[i * 8 + 0] += rs[0] + b0.x; v[i * 8 + 1] += rs[1] + b0.y; v[i * 8 + 2] += rs[2] + b0.z; v[i * 8 + 3] += rs[3] + b0.w;
           v[i * 8 + 4] += rs[4] + b1.x; v[i * 8 + 5] += rs[5] + b1.y; v[i * 8 + 6] += rs[6] + b1.z; v[i * 8 + 7] += rs[7] + b1.w;
         }
@@ -542,6 +554,19 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
         // ---------------- transformer layers
         for (int l = 0; l < NL; ++l) {
           const float* lp = P.lparams + (long long)l * P_SIZE;
+          // With 225 KB of shared memory the L1 is a few KB: every parameter read is an L2 round trip.  The hottest one
+          // (linear1's bias, read by 64 GELU epilogues per step) is staged in shared memory once per layer; the first
+          // named barrier of the attention phase orders it before its first use.
+          reinterpret_cast<float4*>(b1s)[wt] = __ldg(reinterpret_cast<const float4*>(lp + P_B1) + wt);
+          if (wt < 64) {                                 // q bias (per head, [h][64]); the k bias drops out of the softmax,
+            const int h = wt >> 4, i4 = wt & 15;        // the v bias is folded into bo' = bo + Wo bv at set-up
+            reinterpret_cast<float4*>(b1s + 1024)[wt] = __ldg(reinterpret_cast<const float4*>(lp + P_BQKV + h * 192) + i4);
+          } else if (wt < 128) {
+            reinterpret_cast<float4*>(b1s + 1280)[wt - 64] = __ldg(reinterpret_cast<const float4*>(lp + P_BO) + (wt - 64));
+          } else if (wt < 192) {
+            reinterpret_cast<float4*>(b1s + 1536)[wt - 128] = __ldg(reinterpret_cast<const float4*>(lp + P_B2) + (wt - 128));
+          }
+          workers_sync();
           for (int h = 0; h < NH; ++h) {
             const int hb = h & 1;
             ph.wait(bars, B_ACCR + 2 * hb); ph.wait(bars, B_ACCR + 2 * hb + 1);
@@ -555,11 +580,13 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
               if (r >= 96) continue;
               __nv_bfloat16* dst = (ch < 2 ? Qs : (ch < 4 ? Ks : Vs)) + r * QLD + (ch & 1) * 32;
               if (r < S) {
-                const float* bq = lp + P_BQKV + h * 192 + ch * 32;
+                if (ch < 2) {
+                  const float* bq = b1s + 1024 + h * 64 + ch * 32;
 #pragma unroll
-                for (int i = 0; i < 32; i += 4) {
-                  const float4 b4 = __ldg(reinterpret_cast<const float4*>(bq + i));
-                  v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
+                  for (int i = 0; i < 32; i += 4) {
+                    const float4 b4 = *reinterpret_cast<const float4*>(bq + i);
+                    v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
+                  }
                 }
 #pragma unroll
                 for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(dst + i * 8) = pack8(v + i * 8);
@@ -641,7 +668,7 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
             if (hb == 1 && lane == 0) mbar_arrive(&bars[B_BUFR + (h >> 1)]);
             lap(PF_W_ATT);
           }
-          layernorm_epilogue(lp + P_BO, lp + P_G1, lp + P_BE1);
+          layernorm_epilogue(b1s + 1280, lp + P_G1, lp + P_BE1);
           // ---- FFN: GELU epilogue per 128-unit chunk -> BUF half (c & 1) as the A operand of linear2
           for (int c = 0; c < 8; ++c) {
             const int qd = 2 + (c & 1);
@@ -649,24 +676,35 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
             ph.wait(bars, B_BUFF + (c & 1));
             lap(PF_W_GELU_WAIT);
             tcgen05_fence_after();
-#pragma unroll 1
-            for (int ci = 0; ci < 2; ++ci) {
-              const int cc0 = sub * 64 + ci * 32;        // column inside the chunk
-              tmem_ld32(tlane + qd * 128 + cc0, v);
-              const float* b1 = lp + P_B1 + c * 128 + cc0;
+            {
+              float va[32], vb[32];
+              const int cc0 = sub * 64;                  // column inside the chunk
+              tmem_ld32_issue(tlane + qd * 128 + cc0, va); tmem_ld32_issue(tlane + qd * 128 + cc0 + 32, vb);
+              tmem_ld_wait(); tie32(va); tie32(vb);
+              tcgen05_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&bars[B_ACCF + qd]);      // accumulator free: values are in registers now
+              const float* b1 = b1s + c * 128 + cc0;
 #pragma unroll
               for (int i = 0; i < 32; i += 4) {
-                const float4 b4 = __ldg(reinterpret_cast<const float4*>(b1 + i));
-                v[i] = gelu_fast(v[i] + b4.x); v[i + 1] = gelu_fast(v[i + 1] + b4.y);
-                v[i + 2] = gelu_fast(v[i + 2] + b4.z); v[i + 3] = gelu_fast(v[i + 3] + b4.w);
+                const float4 ba = *reinterpret_cast<const float4*>(b1 + i), bb = *reinterpret_cast<const float4*>(b1 + 32 + i);
+                va[i] = gelu_fast(va[i] + ba.x); va[i + 1] = gelu_fast(va[i + 1] + ba.y);
+                va[i + 2] = gelu_fast(va[i + 2] + ba.z); va[i + 3] = gelu_fast(va[i + 3] + ba.w);
+                vb[i] = gelu_fast(vb[i] + bb.x); vb[i + 1] = gelu_fast(vb[i + 1] + bb.y);
+                vb[i + 2] = gelu_fast(vb[i + 2] + bb.z); vb[i + 3] = gelu_fast(vb[i + 3] + bb.w);
               }
 #pragma unroll
-              for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(BUF + a_off(r, (c & 1) * 128 + cc0 + i * 8)) = pack8(v + i * 8);
+              for (int i = 0; i < 4; ++i) {
+                *reinterpret_cast<uint4*>(BUF + a_off(r, (c & 1) * 128 + cc0 + i * 8)) = pack8(va + i * 8);
+                *reinterpret_cast<uint4*>(BUF + a_off(r, (c & 1) * 128 + cc0 + 32 + i * 8)) = pack8(vb + i * 8);
+              }
             }
-            release_acc(qd, -1, false, c & 1);
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars[B_BUFR + (c & 1)]);
             lap(PF_W_GELU);
           }
-          layernorm_epilogue(lp + P_B2, lp + P_G2, lp + P_BE2);
+          layernorm_epilogue(b1s + 1536, lp + P_G2, lp + P_BE2);
           debug_dump(l + 1, clip);
         }
 
@@ -709,7 +747,7 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
         workers_sync();                                  // x_{t-1} of every frame is visible to the staging loop of the next step
       }
     }
-    if (prof) for (int i = PF_W_STAGE; i < PF_COUNT; ++i) P.prof[i] = pf[i];
+    if constexpr (PROF) { if (prof) for (int i = PF_W_STAGE; i < PF_COUNT; ++i) P.prof[i] = pf[i]; }
   }
   tcgen05_fence_before();
   __syncthreads();

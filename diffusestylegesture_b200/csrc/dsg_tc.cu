@@ -131,6 +131,15 @@ static int clip_setup(dsg_engine* e) {
       for (int part = 0; part < 3; ++part)
         for (int i = 0; i < 64; ++i) p[P_BQKV + h * 192 + part * 64 + i] = tmp[part * D + h * HD + i];
     CUDA_TRY(fetch(w[L_OUTPROJ_B], p + P_BO, D)); CUDA_TRY(fetch(w[L_N1_W], p + P_G1, D)); CUDA_TRY(fetch(w[L_N1_B], p + P_BE1, D));
+    {   // the v bias passes through the softmax average unchanged: bo' = bo + Wo bv (the k bias cancels in the softmax)
+      std::vector<float> wo((size_t)D * D);
+      CUDA_TRY(fetch(w[L_OUTPROJ_W], wo.data(), wo.size()));
+      for (int o = 0; o < D; ++o) {
+        double acc = 0.0;
+        for (int i = 0; i < D; ++i) acc += (double)wo[(size_t)o * D + i] * (double)tmp[2 * D + i];
+        p[P_BO + o] += (float)acc;
+      }
+    }
     CUDA_TRY(fetch(w[L_FF1_B], p + P_B1, F));    CUDA_TRY(fetch(w[L_FF2_B], p + P_B2, D));
     CUDA_TRY(fetch(w[L_N2_W], p + P_G2, D));     CUDA_TRY(fetch(w[L_N2_B], p + P_BE2, D));
   }
@@ -144,7 +153,8 @@ static int clip_setup(dsg_engine* e) {
   TRY(make_tmap(&t->tm_c128, t->wK256, rows256, D, 128));
   TRY(make_tmap(&t->tm_c64, t->wK256, rows256, D, 64));
   TRY(make_tmap(&t->tm_cw2, t->wK1024, (uint64_t)NL * D, F, 128));
-  CUDA_TRY(cudaFuncSetAttribute(clip::clip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  CUDA_TRY(cudaFuncSetAttribute(clip::clip_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  CUDA_TRY(cudaFuncSetAttribute(clip::clip_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   t->clip_ok = true;
   return DSG_OK;
 }
@@ -159,7 +169,8 @@ static int clip_run(dsg_engine* e, int B, float* xd, int n_run, int first_index,
   p.prof = getenv("DSG_CLIP_PROF") ? t->prof : nullptr;
   p.dbg = e->dbg; p.dbg_slot = (long long)e->d.max_batch * e->S * e->d.latent_dim; p.debug = e->debug ? 1 : 0;
   const int grid = B < e->num_sms ? B : e->num_sms;
-  clip::clip_kernel<<<grid, 384, clip::SMEM_BYTES, st>>>(t->tm_cin, t->tm_c128, t->tm_c64, t->tm_cw2, p);
+  if (p.prof) clip::clip_kernel<true><<<grid, 384, clip::SMEM_BYTES, st>>>(t->tm_cin, t->tm_c128, t->tm_c64, t->tm_cw2, p);
+  else clip::clip_kernel<false><<<grid, 384, clip::SMEM_BYTES, st>>>(t->tm_cin, t->tm_c128, t->tm_c64, t->tm_cw2, p);
   e->launches++;
   CUDA_TRY(cudaGetLastError());
   return DSG_OK;
