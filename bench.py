@@ -305,7 +305,26 @@ def main():
                         "launches_per_segment": nl, "us_per_ddpm_step": ms * 1e3 / diffusion.num_timesteps,
                         "note": "segment call timed with CUDA events (conditioning GEMMs + x_T draw + the loop kernel); "
                                 "FLOPs = reference's 2*M*N*K count, excludes padding (89 -> 128 token rows) and hoisted terms"}
+            # HBM traffic of the launch: x_t is read twice and written once, the pre-drawn noise is written and read once
+            # per clip-step (everything else is on chip or L2-resident weights): ncu measured 1.72 MB per clip-step
+            # (profiles/r01_clip_kernel_ncu_full_summary.csv: dram read + write of a 148-clip x 12-step launch)
+            roofline["traffic"] = 1.72e6 * B * diffusion.num_timesteps
+            roofline["traffic_note"] = "bytes per launch = ncu dram__bytes_read+write per clip-step (1.72 MB, r01 capture) x clips x steps"
             log("clip-kernel segment: %.1f ms (%.1f us per DDPM step), %.1f TFLOP/s" % (ms, ms * 1e3 / diffusion.num_timesteps, ach))
+            try:      # where the persistent kernel spends its cycles (instrumented build of the same kernel, 50 steps)
+                os.environ["DSG_CLIP_PROF"] = "1"
+                d50 = create_gaussian_diffusion([50])
+                d50.p_sample_loop(model, shape, clip_denoised=False, model_kwargs={'y': y})
+                torch.cuda.synchronize(dev)
+                ph = eng.clip_profile()
+                mhz = (clk or {}).get("sm_mhz") or 1965.0
+                kernels = {"clip_kernel_phases_us_per_step": {k: v / 50 / mhz for k, v in ph.items()},
+                           "note": "clock64() deltas of CTA 0 (MMA thread: total / waiting for weights / waiting for the workers; "
+                                   "worker thread 0: time per epilogue phase), instrumented build, 50 steps"}
+            except (RuntimeError, NotImplementedError) as ex:
+                sys.stderr.write(f"clip profile unavailable: {ex}\n")
+            finally:
+                os.environ.pop("DSG_CLIP_PROF", None)
         else:
             psteps = min(args.profile_steps, diffusion.num_timesteps - 1)
             try:
