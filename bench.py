@@ -135,6 +135,15 @@ def cpu_baseline(sample_steps, batch, threads):
             "ms_per_denoise_step": per_step * 1e3}
 
 
+def emit(line):
+    """The ONE JSON line goes to the real stdout; everything else that lands on fd 1 (NCCL's version banner, library
+    prints) was redirected to stderr in main()."""
+    os.write(REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+REAL_STDOUT = 1
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
@@ -155,10 +164,14 @@ def run_reference(args, rank, world):
                                    "reference sampler; each bench step = bounded sample extrapolated", "batch": args.ref_batch},
             "cpu_baseline": cb,
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
+    global REAL_STDOUT
+    sys.stdout.flush()
+    REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
@@ -373,7 +386,7 @@ def main():
                            "precision": precision, "parallelism": f"clip-dp{world}", "l2": "flushed between timed iterations (256 MB write)"},
                 "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "kernels": kernels, "cpu_baseline": cb,
                 "clocks": clk}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
