@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libdsg.so")
-SOURCES = ["dsg_engine.cu", "dsg_tc.cu"]
+SOURCES = ["dsg_engine.cu", "dsg_tc.cu", "dsg_wavlm.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 

@@ -42,65 +42,7 @@ struct dsg_tc_state {
   CUtensorMap tm_cin, tm_c128, tm_c64, tm_cw2;
 };
 
-// ---------------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static EncodeTiledFn g_encode = nullptr;
-
-static int get_encode() {
-  if (g_encode) return DSG_OK;
-  void* fn = nullptr;
-  cudaDriverEntryPointQueryResult q;
-  CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
-  if (!fn || q != cudaDriverEntryPointSuccess) return dsg_fail(DSG_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
-  g_encode = (EncodeTiledFn)fn;
-  return DSG_OK;
-}
-
-// bf16 row-major [rows, cols] -> 2-D tensor map with a (box_rows x 64) box and 128-byte swizzle
-static int make_tmap(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
-  TRY(get_encode());
-  if (cols % 8) return dsg_fail(DSG_ERR_BAD_SHAPE, "tensor map: row length %llu not a multiple of 8 bf16", (unsigned long long)cols);
-  const cuuint64_t gdim[2] = {cols, rows};
-  const cuuint64_t gstride[1] = {cols * sizeof(bf16)};
-  const cuuint32_t box[2] = {(cuuint32_t)BK, box_rows};
-  const cuuint32_t estr[2] = {1, 1};
-  const CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
-                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return dsg_fail(DSG_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu", (int)r,
-                                         (unsigned long long)rows, (unsigned long long)cols);
-  return DSG_OK;
-}
-
-template <int BN, int STAGES, int EPI>
-static int launch_tc(dsg_engine* e, const CUtensorMap& a, const CUtensorMap& b, const TcEpiArgs& ep, int n_tiles, cudaStream_t st) {
-  static bool configured = false;
-  constexpr int smem = TcSmem<BN, STAGES>::TOTAL;
-  if (!configured) {
-    CUDA_TRY(cudaFuncSetAttribute(tc_gemm_kernel<BN, STAGES, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
-  }
-  dim3 grid((ep.M + BM - 1) / BM, n_tiles);
-  tc_gemm_kernel<BN, STAGES, EPI><<<grid, 256, smem, st>>>(a, b, ep);
-  e->launches++;
-  CUDA_TRY(cudaGetLastError());
-  return DSG_OK;
-}
-
-template <typename T>
-static int dalloc0(T** p, size_t n) {
-  CUDA_TRY(cudaMalloc((void**)p, n * sizeof(T)));
-  CUDA_TRY(cudaMemset(*p, 0, n * sizeof(T)));
-  return DSG_OK;
-}
-
-static int pack_w(const float* src, bf16* dst, int rows, int cols, long long ld, int rows_pad, int cols_pad) {
-  pack_weight_bf16_kernel<<<296, 256>>>(src, dst, rows, cols, ld, rows_pad, cols_pad);
-  CUDA_TRY(cudaGetLastError());
-  return DSG_OK;
-}
+#include "dsg_tc_host.cuh"
 
 // ---------------------------------------------------------------------------------------------------
 // clip kernel set-up: weight slabs in the row order clip::R_* expects, fp32 parameter blocks, tensor maps

@@ -22,11 +22,16 @@ enum TcEpi {
   EPI_BF16 = 2,     // bf16 [M, ldc] = acc + bias                    in_proj of self-attention
   EPI_GELU = 3,     // bf16 [M, ldc] = gelu_erf(acc + bias)          linear1 + activation
   EPI_LN = 4,       // xs = LayerNorm(acc + bias + xs) -> fp32 + bf16 copies   out_proj / linear2 + norm (post-norm layer)
-  EPI_HEAD = 5      // x0 = acc + bias; posterior update of x (fp32 [B,J,T]) + bf16 repack [B,S,Jpad]   OutputProcess + p_sample
+  EPI_HEAD = 5,     // x0 = acc + bias; posterior update of x (fp32 [B,J,T]) + bf16 repack [B,S,Jpad]   OutputProcess + p_sample
+  EPI_RESID = 6,    // fp32 [M, ldc] += acc + bias                 out_proj / fc2 of a pre-norm layer (WavLM)
+  EPI_PCONV = 7     // fp32 [M, ldc] += gelu(acc + bias)           grouped positional conv (WavLM)
 };
 
 struct TcEpiArgs {
   int M, N, K;                 // logical GEMM sizes (N = valid output columns; tile columns beyond N are skipped)
+  // batched (3-D A map) form: blockIdx.z = batch * z_div + group; rows m < rows_per_z of that batch; output row =
+  // batch * rows_per_z + m; the group selects B rows / output columns [group * BN, +BN).  rows_per_z == 0: flat 2-D GEMM.
+  int rows_per_z, z_div;
   const float* bias;           // [N]
   // EPI_F32 / EPI_BF16 / EPI_GELU
   void* out; int ldc;
@@ -61,6 +66,10 @@ DSG_DEVINL void mbar_wait(uint64_t* bar, uint32_t parity) {
 DSG_DEVINL void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+DSG_DEVINL void tma_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+               ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 DSG_DEVINL void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 DSG_DEVINL void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -193,7 +202,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   float* red = reinterpret_cast<float*>(smem + SM::RED_OFF);     // [2 halves][128 rows][2] LayerNorm partials
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  const int zdiv = ep.z_div > 0 ? ep.z_div : 1;
+  const int zb = (int)blockIdx.z / zdiv, zg = (int)blockIdx.z - zb * zdiv;
+  const int m0 = blockIdx.x * BM, n0 = (blockIdx.y + zg) * BN;
   const int num_kb = (ep.K + BK - 1) / BK;
 
   if (warp == 0 && lane == 0) {
@@ -223,7 +234,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_wait(&empty_bar[s], ph ^ 1u);
       mbar_expect_tx(&full_bar[s], SM::STAGE_BYTES);
       uint8_t* a_dst = smem + s * SM::STAGE_BYTES;
-      tma_load_2d(a_dst, &tmA, &full_bar[s], kb * BK, m0);
+      if (ep.rows_per_z > 0) tma_load_3d(a_dst, &tmA, &full_bar[s], kb * BK, m0, (int)blockIdx.z);
+      else tma_load_2d(a_dst, &tmA, &full_bar[s], kb * BK, m0);
       tma_load_2d(a_dst + SM::A_BYTES, &tmB, &full_bar[s], kb * BK, n0);
     }
   } else if (warp == 1 && lane == 0) {
@@ -253,12 +265,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tcgen05_fence_after();
   const int wq = warp & 3, half = warp >> 2;
   const int rloc = wq * 32 + lane;
-  const int row = m0 + rloc;
-  const bool row_ok = row < ep.M;
+  const int row = ep.rows_per_z > 0 ? zb * ep.rows_per_z + m0 + rloc : m0 + rloc;
+  const bool row_ok = ep.rows_per_z > 0 ? (m0 + rloc < ep.rows_per_z) : (row < ep.M);
   const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16);
   float v[32];
 
-  if constexpr (EPI == EPI_F32 || EPI == EPI_BF16 || EPI == EPI_GELU) {
+  if constexpr (EPI == EPI_F32 || EPI == EPI_BF16 || EPI == EPI_GELU || EPI == EPI_RESID || EPI == EPI_PCONV) {
 #pragma unroll 1
     for (int c = half * 32; c < BN; c += 64) {
       tmem_ld32(taddr + c, v);
@@ -274,11 +286,24 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
         for (int i = 0; i < 32; ++i) if (ep.bias && n + i < ep.N) v[i] += __ldg(ep.bias + n + i);
       }
-      if constexpr (EPI == EPI_GELU) {
+      if constexpr (EPI == EPI_GELU || EPI == EPI_PCONV) {
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = gelu_fast(v[i]);
       }
-      if constexpr (EPI == EPI_F32) {
+      if constexpr (EPI == EPI_RESID || EPI == EPI_PCONV) {
+        float* o = reinterpret_cast<float*>(ep.out) + (long long)row * ep.ldc + n;
+        if (n + 32 <= ep.N && (ep.ldc & 3) == 0) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            float4 t = *reinterpret_cast<float4*>(o + i);
+            t.x += v[i]; t.y += v[i + 1]; t.z += v[i + 2]; t.w += v[i + 3];
+            *reinterpret_cast<float4*>(o + i) = t;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) if (n + i < ep.N) o[i] += v[i];
+        }
+      } else if constexpr (EPI == EPI_F32) {
         float* o = reinterpret_cast<float*>(ep.out) + (long long)row * ep.ldc + n;
         if (n + 32 <= ep.N && (ep.ldc & 3) == 0) {
 #pragma unroll

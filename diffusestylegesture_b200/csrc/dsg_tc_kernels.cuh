@@ -4,7 +4,7 @@
 #include "dsg_common.cuh"
 
 // fp32 [rows, cols] (leading dim ld_src) -> bf16 [rows_pad, cols_pad], zero padding.
-__global__ void __launch_bounds__(256) pack_weight_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
+static __global__ void __launch_bounds__(256) pack_weight_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
                                                               int rows, int cols, long long ld_src, int rows_pad, int cols_pad) {
   const long long total = (long long)rows_pad * cols_pad;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
@@ -15,7 +15,7 @@ __global__ void __launch_bounds__(256) pack_weight_bf16_kernel(const float* __re
 
 // x fp32 [B, J, T]  ->  xb bf16 [B, S, Jpad] rows 1..T (row 0 and the pad columns stay zero): the K-major A
 // operand of the input GEMM.  32x32 tile transpose through shared memory; both sides coalesced.
-__global__ void __launch_bounds__(256) pack_x_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ xb,
+static __global__ void __launch_bounds__(256) pack_x_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ xb,
                                                          int J, int T, int S, int Jpad) {
   __shared__ float tile[32][33];
   const int b = blockIdx.z, j0 = blockIdx.x * 32, f0 = blockIdx.y * 32;
@@ -38,7 +38,7 @@ __global__ void __launch_bounds__(256) pack_x_bf16_kernel(const float* __restric
 // (ALU/MUFU work under tensor-pipe work).  Skipped when the step adds no noise (index 0 / DDIM).
 struct NoiseArgs { float* z; const long long* clip_ids; StepRef step; int B; long long per_clip; int sampler; };
 
-__global__ void __launch_bounds__(256) noise_tile_kernel(const NoiseArgs a) {
+static __global__ void __launch_bounds__(256) noise_tile_kernel(const NoiseArgs a) {
   const int index = a.step.index();
   if (index == 0 || a.sampler != 0) return;
   const uint32_t draw = (uint32_t)(1 + a.step.k());
@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(256) noise_tile_kernel(const NoiseArgs a) {
   }
 }
 
-__global__ void bump_step_kernel(LoopParams* lp) { lp->k += 1; }
+static __global__ void bump_step_kernel(LoopParams* lp) { lp->k += 1; }
 
 // ---------------------------------------------------------------------------------------------------
 // Global self-attention on tensor cores (nn.TransformerEncoderLayer's SDPA: softmax(q k^T / sqrt(hd)) v, no mask;

@@ -19,7 +19,8 @@ SAMPLER = {"ddpm": 0, "ddim": 1}
 
 EXPORTS = ["dsg_engine_create", "dsg_engine_destroy", "dsg_set_schedule", "dsg_set_conditioning", "dsg_denoise",
            "dsg_posterior_step", "dsg_sample_loop", "dsg_stitch_segment", "dsg_kernel_launch_count",
-           "dsg_debug_read", "dsg_profile", "dsg_profile_read", "dsg_profile_tag_name", "dsg_selftest_gemm", "dsg_last_error", "dsg_version"]
+           "dsg_debug_read", "dsg_profile", "dsg_profile_read", "dsg_profile_tag_name", "dsg_selftest_gemm", "dsg_wavlm_create", "dsg_wavlm_forward", "dsg_wavlm_frames",
+           "dsg_wavlm_launch_count", "dsg_wavlm_destroy", "dsg_last_error", "dsg_version"]
 
 
 class _Desc(ctypes.Structure):

@@ -10,7 +10,8 @@ Differences from the reference, all additive:
     reproduces the reference semantics exactly, including the n == 1 "blend" quirk (sample.py:284-288);
   * conditioning may be given as precomputed WavLM-shaped features (the WavLM-Large forward itself is the
     next row of the scope table); when a raw wav and a WavLM module are given the
-    reference's ``wav2wavlm`` contract (extract_features + linear interpolation to n_poses) is kept;
+    reference's ``wav2wavlm`` contract (extract_features + linear interpolation to n_poses) is kept — with
+    ``diffusestylegesture_b200.wavlm.WavLM`` that forward runs in libdsg too (dsg_wavlm_forward);
   * new optional YAML keys: ``precision`` (bf16|fp32), ``sampler`` (ddpm|ddim), ``timestep_respacing``.
 """
 import argparse
@@ -70,6 +71,8 @@ def _get(args, key, default):
 def wav2wavlm(model, wav_input_16khz, device, n_poses=88):
     """sample.py:44-48 (ZEGGS: no waveform layer-norm).  ``model`` is any WavLM-Large module exposing
     ``extract_features``; its forward is outside this round's scope (see module docstring)."""
+    if hasattr(model, "wav2wavlm"):          # diffusestylegesture_b200.wavlm.WavLM: fused in libdsg
+        return model.wav2wavlm(wav_input_16khz.to(device), n_poses)
     rep = model.extract_features(wav_input_16khz.to(device))[0]
     return F.interpolate(rep.transpose(1, 2), size=n_poses, align_corners=True, mode='linear').transpose(1, 2)
 

@@ -133,6 +133,21 @@ int dsg_profile(dsg_engine* e, int32_t enable);
 int dsg_profile_read(dsg_engine* e, int32_t tag, int64_t* count, double* total_ms);
 const char* dsg_profile_tag_name(int32_t tag);
 
+/* ---- WavLM-Large conditioning front-end (reference main/mydiffusion_zeggs/sample.py:30-48, WavLM/WavLM.py:323-375) ----
+ * Replaces wavlm_init + wav2wavlm: `weights[i]` = fp32 tensor i of diffusestylegesture_b200/wavlm_config.py:
+ * wavlm_state_dict_spec (the reference WavLM state_dict keys); `pos_bias` = compute_bias(L, L) of layer 0
+ * ([heads, L, L] fp32, L = frames for n_samples; modules_WavLM.py:444-455), evaluated once by the host mirror.
+ * dsg_wavlm_forward: wav [batch, n_samples] fp32 (host or device) -> out [batch, n_poses, 1024] (features linearly
+ * interpolated to n_poses frames, align_corners = True), or [batch, L, 1024] when n_poses == 0 (extract_features()[0]).
+ * Batches larger than max_batch are processed in sub-batches. */
+typedef struct dsg_wavlm dsg_wavlm;
+int dsg_wavlm_create(int32_t device, int32_t max_batch, int32_t n_samples, const float* const* weights, int32_t n_weights,
+                     const float* pos_bias, dsg_wavlm** out);
+int dsg_wavlm_forward(dsg_wavlm* m, int32_t batch, const float* wav, int32_t n_poses, float* out, void* stream);
+int32_t dsg_wavlm_frames(const dsg_wavlm* m);
+int64_t dsg_wavlm_launch_count(const dsg_wavlm* m);
+void dsg_wavlm_destroy(dsg_wavlm* m);
+
 /* Stand-alone check of the tcgen05 GEMM building block (tests): C[M,N] = bf16(A[M,K]) * bf16(W[N,K])^T + bias, fp32
  * accumulate and output.  bn = 128 or 256 (UMMA N); K a multiple of 8.  Host or device pointers. */
 int dsg_selftest_gemm(int32_t device, int32_t bn, int32_t M, int32_t N, int32_t K, const float* A, const float* W,
