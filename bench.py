@@ -135,6 +135,42 @@ def cpu_baseline(sample_steps, batch, threads):
             "ms_per_denoise_step": per_step * 1e3}
 
 
+WAVLM_FLOP_PER_SEGMENT = 162.5e9      # 70,400 samples -> 219 frames: convs 21.6 + pos-conv 3.7 + 24 layers 137 GFLOP
+
+
+def bench_wavlm(dev, batch, peaks, frames_per_s_per_gpu):
+    from diffusestylegesture_b200.wavlm import WavLM
+    from diffusestylegesture_b200.wavlm_config import WAVLM_LARGE, synthetic_wavlm_state_dict, synthetic_wav
+    log("wavlm: building synthetic WavLM-Large (315 M parameters)")
+    m = WavLM(max_batch=batch)
+    m.load_state_dict(synthetic_wavlm_state_dict(WAVLM_LARGE, seed=0))
+    m.to(dev).eval()
+    wav = synthetic_wav(batch, 70400).pin_memory()
+    for _ in range(3):
+        m.wav2wavlm(wav, 88)
+    torch.cuda.synchronize(dev)
+    l0 = m.launches
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    K = 10
+    a.record()
+    for _ in range(K):
+        out = m.wav2wavlm(wav, 88)
+    b.record()
+    torch.cuda.synchronize(dev)
+    ms = a.elapsed_time(b) / K
+    assert bool(torch.isfinite(out).all())
+    ach = WAVLM_FLOP_PER_SEGMENT * batch / (ms * 1e-3) / 1e12
+    seg_per_s = batch / (ms * 1e-3)
+    res = {"segments_per_call": batch, "ms_per_call": ms, "segments_per_s": seg_per_s, "frames_per_s": seg_per_s * 80,
+           "tflops": ach, "frac_of_sustained_bf16": ach / peaks["bf16_tflops_sustained"], "launches_per_call": (m.launches - l0) // K,
+           "h2d_bytes_per_call": int(wav.numel() * 4),
+           "share_of_clip_time": (frames_per_s_per_gpu / (seg_per_s * 80)) if frames_per_s_per_gpu else None,
+           "note": "one 70,400-sample window per 80 new frames; share_of_clip_time = WavLM time / diffusion time for the same frames"}
+    log("wavlm: %.2f ms per %d segments, %.0f TFLOP/s" % (ms, batch, ach))
+    m.close()
+    return res
+
+
 def emit(line):
     """The ONE JSON line goes to the real stdout; everything else that lands on fd 1 (NCCL's version banner, library
     prints) was redirected to stderr in main()."""
@@ -186,6 +222,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--profile-steps", type=int, default=40)
+    ap.add_argument("--no-wavlm", action="store_true", help="skip the side measurement of the WavLM-Large conditioning forward")
+    ap.add_argument("--wavlm-batch", type=int, default=32)
     args = ap.parse_args()
 
     from diffusestylegesture_b200.distributed import init_from_env, barrier_max_ms, gather_motions
@@ -293,8 +331,8 @@ def main():
     # achieved = algorithmic denoiser FLOPs of the launch (1.3155 GFLOP x clips x steps, as written in the
     # reference) / duration.  DSG_TC_MODE=kernels / fp32: per-kernel-class event timing of the multi-kernel path.
     roofline, kernels = None, None
+    peaks = load_peaks() if rank == 0 else None
     if rank == 0:
-        peaks = load_peaks()
         y = dict(conds[0], audio=feats_dev[0], noise_seed=123456, segment=0, clip_ids=clip_ids)
         shape = (B, g.njoints, 1, g.n_poses)
         clip_mode = precision == "bf16" and os.environ.get("DSG_TC_MODE", "clip") != "kernels"
@@ -369,6 +407,15 @@ def main():
                     kernels["posterior"]["hbm_gbs"] = gbs
                     kernels["posterior"]["hbm_frac_of_measured_peak"] = gbs / peaks["hbm_gbs"]
 
+    # ---- side measurement (not part of `value`): the WavLM-Large conditioning forward of the same clips, raw 16 kHz
+    # waveform in pinned host memory -> [segments, 88, 1024] features on the device, through dsg_wavlm_forward
+    wavlm = None
+    if rank == 0 and not args.no_wavlm and precision == "bf16":
+        try:
+            wavlm = bench_wavlm(dev, args.wavlm_batch, peaks, value / world)
+        except (RuntimeError, NotImplementedError) as ex:
+            sys.stderr.write(f"wavlm measurement unavailable: {ex}\n")
+
     cb = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         log("cpu baseline (oracle port, %d threads)" % host_threads())
@@ -384,8 +431,8 @@ def main():
                                        "[B,88,1024] per segment, synthetic weights (9.0 M params)",
                            "clips_per_gpu": B, "global_clips": world * B, "segments": nseg, "ddpm_steps": diffusion.num_timesteps,
                            "precision": precision, "parallelism": f"clip-dp{world}", "l2": "flushed between timed iterations (256 MB write)"},
-                "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "kernels": kernels, "cpu_baseline": cb,
-                "clocks": clk}
+                "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "kernels": kernels, "wavlm": wavlm,
+                "cpu_baseline": cb, "clocks": clk}
         emit(line)
     if world > 1:
         dist.barrier()

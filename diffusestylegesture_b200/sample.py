@@ -8,10 +8,9 @@ Differences from the reference, all additive:
   * every diffusion step runs inside libdsg (``diffusion.p_sample_loop`` -> one C call per segment);
   * ``inference_batch`` runs B independent clips in lock-step (the reference is batch 1 only); per clip it
     reproduces the reference semantics exactly, including the n == 1 "blend" quirk (sample.py:284-288);
-  * conditioning may be given as precomputed WavLM-shaped features (the WavLM-Large forward itself is the
-    next row of the scope table); when a raw wav and a WavLM module are given the
-    reference's ``wav2wavlm`` contract (extract_features + linear interpolation to n_poses) is kept — with
-    ``diffusestylegesture_b200.wavlm.WavLM`` that forward runs in libdsg too (dsg_wavlm_forward);
+  * the WavLM-Large conditioning forward (``wavlm_init`` / ``wav2wavlm``, sample.py:28-48) runs in libdsg too
+    (dsg_wavlm_forward) and takes all segments of a clip as one batch; conditioning may also be given as
+    precomputed WavLM-shaped features;
   * new optional YAML keys: ``precision`` (bf16|fp32), ``sampler`` (ddpm|ddim), ``timestep_respacing``.
 """
 import argparse
@@ -68,9 +67,21 @@ def _get(args, key, default):
         return default
 
 
+def wavlm_init(device=None, wavlm_model_path='./WavLM/WavLM-Large.pt', max_batch=16):
+    """sample.py:28-39: load ``WavLM-Large.pt`` ({'cfg', 'model'}) into the engine-backed WavLM mirror."""
+    from .wavlm import WavLM, WavLMConfig
+    checkpoint = torch.load(wavlm_model_path, map_location=torch.device('cpu'))
+    model = WavLM(WavLMConfig(checkpoint['cfg']), max_batch=max_batch)
+    model.load_state_dict(checkpoint['model'])
+    model = model.to(device if device is not None else torch.device('cuda:0'))
+    model.eval()
+    return model
+
+
 def wav2wavlm(model, wav_input_16khz, device, n_poses=88):
-    """sample.py:44-48 (ZEGGS: no waveform layer-norm).  ``model`` is any WavLM-Large module exposing
-    ``extract_features``; its forward is outside this round's scope (see module docstring)."""
+    """sample.py:44-48 (ZEGGS: no waveform layer-norm).  ``model`` is the engine-backed
+    ``diffusestylegesture_b200.wavlm.WavLM`` (fused forward + interpolation in libdsg) or any module exposing
+    ``extract_features``."""
     if hasattr(model, "wav2wavlm"):          # diffusestylegesture_b200.wavlm.WavLM: fused in libdsg
         return model.wav2wavlm(wav_input_16khz.to(device), n_poses)
     rep = model.extract_features(wav_input_16khz.to(device))[0]
@@ -153,10 +164,11 @@ def inference(args, wavlm_model, audio, sample_fn, model, n_frames=0, smoothing=
         dev = next(model.parameters()).device
         chunks = torch.from_numpy(audio).to(torch.float32).reshape(nseg, int(stride * 16000 / 20))
         pad = int(n_seed * 16000 / 20)
-        features = []
-        for i in range(nseg):                                                     # sample.py:238-251
-            head = torch.zeros(pad) if i == 0 else chunks[i - 1, -pad:]
-            features.append(wav2wavlm(wavlm_model, torch.cat((head, chunks[i]))[None], dev, n_poses))
+        # sample.py:238-251: segment i hears [last n_seed frames of segment i-1 (zeros for i = 0) | its own stride frames];
+        # the segments are independent for WavLM, so they go through it as ONE batch
+        wavs = torch.stack([torch.cat((torch.zeros(pad) if i == 0 else chunks[i - 1, -pad:], chunks[i])) for i in range(nseg)])
+        feats = wav2wavlm(wavlm_model, wavs, dev, n_poses)
+        features = [feats[i:i + 1] for i in range(nseg)]
     else:
         nseg = len(features)
         n_frames = nseg * (n_poses - n_seed)
@@ -215,10 +227,9 @@ def main(args, save_dir, model_path, audio_path=None, mfcc_path=None, audiowavlm
     print(style)
     audio = None
     if features is None:
-        if wavlm_model is None:
-            raise NotImplementedError(
-                "the WavLM-Large forward is not part of this engine yet (SURVEY.md section 8(f).1): pass "
-                "`wavlm_model` (any module with extract_features) or precomputed `features`")
+        if wavlm_model is None:                                                  # sample.py:383
+            wavlm_model = wavlm_init(torch.device('cuda:' + str(args.gpu)),
+                                     _get(args, 'wavlm_path', './WavLM/WavLM-Large.pt'))
         audio, _ = load_wav_16k(audiowavlm_path)
     return inference(args, wavlm_model, audio, sample_fn, model, n_frames=max_len, smoothing=True, SG_filter=True,
                      minibatch=True, skip_timesteps=0, style=style, seed=123456, features=features, save_dir=save_dir)

@@ -35,3 +35,32 @@ def test_wav2wavlm_vs_reference_golden(gold_dir):
     assert m.launches > 0
     with pytest.raises(NotImplementedError):
         m.extract_features(wav, mask=True)
+
+
+def test_wav_to_bvh_through_both_engines(tmp_path):
+    """Raw 16 kHz waveform -> WavLM (libdsg) -> 2 segments x 20-step DDPM (libdsg) -> BVH, the reference `inference` call
+    (sample.py:210-338) with every device op in the engine; batched segment conditioning equals per-segment calls."""
+    from diffusestylegesture_b200 import sample as S
+    from diffusestylegesture_b200.config import ZEGGS
+    from diffusestylegesture_b200.mdm import MDM
+    from diffusestylegesture_b200.model_util import create_gaussian_diffusion, load_model_wo_clip
+    from diffusestylegesture_b200.synthetic import synthetic_state_dict
+    wm = WavLM(max_batch=4)
+    wm.load_state_dict(synthetic_wavlm_state_dict(WAVLM_LARGE, seed=0))
+    wm.to('cuda:0').eval()
+    model = MDM(njoints=ZEGGS.njoints, cond_mode='cross_local_attention3_style1', audio_feat='wavlm', n_seed=8, precision='bf16', max_batch=1)
+    load_model_wo_clip(model, synthetic_state_dict(ZEGGS, seed=0))
+    model.to('cuda:0').eval()
+    d = create_gaussian_diffusion([20])
+    audio = synthetic_wav(1, 160 * 800 + 1234)[0].numpy()             # a little more than 2 strides of 80 frames
+    path, poses = S.inference(S.Config(n_poses=88, audio_feat="wavlm"), wm, audio, d.p_sample_loop, model, n_frames=0, smoothing=True,
+                              SG_filter=True, minibatch=True, style=[1, 0, 0, 0, 0, 0], seed=7, save_dir=str(tmp_path))
+    assert poses.shape == (160 - 8, 1141) and np.isfinite(poses).all()
+    lines = open(path).read().splitlines()
+    assert lines[0] == "HIERARCHY" and any(l.startswith("Frames: 152") for l in lines)
+    # batched conditioning == per-segment conditioning (reference loop order, sample.py:238-251)
+    a = torch.from_numpy(audio[:160 * 800]).reshape(2, 64000)
+    w0 = torch.cat((torch.zeros(6400), a[0]))[None]
+    w1 = torch.cat((a[0, -6400:], a[1]))[None]
+    f01 = S.wav2wavlm(wm, torch.cat((w0, w1)), 'cuda:0', 88)
+    assert torch.equal(f01[0], S.wav2wavlm(wm, w0, 'cuda:0', 88)[0]) and torch.equal(f01[1], S.wav2wavlm(wm, w1, 'cuda:0', 88)[0])
