@@ -8,9 +8,10 @@
 //                            4..11 = 8 worker warps: A-operand staging, all epilogues, both attentions.
 // Tensor memory (512 columns) = 4 quarters of 128 fp32 columns (Q0..Q3), handed back and forth per op with
 // ready/free mbarriers.  Shared memory:
-//   XS  [128 x 256] bf16, UMMA K-major SWIZZLE_128B (4 k-tiles)  — the residual stream AND the A operand
+//   XS  [128 x 256] bf16, UMMA K-major SWIZZLE_128B (4 k-tiles)  — the residual stream AND the A operand; rows 96..127
+//                                        carry no token, so k-tile 0's 4 KB there holds the layer's LayerNorm gains/biases
 //   BUF [128 x 256] bf16, same format — A ring of the input GEMM / rope'd h for local attention /
-//                                        attention output (A of out_proj) / FFN hidden chunk (A of linear2)
+//                                        attention output (A of out_proj) / FFN hidden chunk (fp16, A of linear2)
 //   W   3 x 16 KB weight stages ([128 or 64 rows] x 64 k), TMA + mbarrier ring
 //   Qs/Ks/Vs [96][72] bf16 per-head staging for the mma.sync attention; LayerNorm partials; barriers.
 #pragma once
@@ -32,7 +33,8 @@ constexpr int OFF_Q = OFF_W + NS * WSTAGE;
 constexpr int OFF_K = OFF_Q + 96 * QLD * 2;
 constexpr int OFF_V = OFF_K + 96 * QLD * 2;
 constexpr int OFF_RED = OFF_V + 96 * QLD * 2;
-constexpr int OFF_B1 = OFF_RED + 2048;           // per-layer parameters staged in shared memory (fp32): b1[1024] | bq[256] | bo'[256] | b2[256]
+constexpr int OFF_B1 = OFF_RED + 2048;           // per-layer parameters staged in shared memory: b1[1024] fp16 | 2 KB spare | fp32 bq[256] | bo'[256] | b2[256]
+constexpr int OFF_LNP = OFF_XS + 12288;          // rows 96..127 of XS k-tile 0 (never a token): fp32 g1[256] | be1[256] | g2[256] | be2[256]
 constexpr int OFF_BAR = OFF_B1 + 4096 + 3072;
 constexpr int SMEM_BYTES = OFF_BAR + 512 + 1024;
 constexpr int ZLD = 264;                    // rope'd h staging row stride (bf16), lives in BUF: 104 rows x 528 B
@@ -85,6 +87,16 @@ DSG_DEVINL uint4 pack8(const float* v) {
   uint4 u;
   u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]); u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
   return u;
+}
+// GELU(x) = 0.5 x (1 + tanh(sqrt(2/pi) (x + 0.044715 x^3))) on two fp16 lanes; saturates correctly when x^2 overflows
+DSG_DEVINL uint32_t gelu_h2(const __half2 x) {
+  const __half2 c1 = __floats2half2_rn(0.0356774081f, 0.0356774081f), c0 = __floats2half2_rn(0.7978845608f, 0.7978845608f);
+  const __half2 u = __hmul2(__hfma2(__hmul2(x, x), c1, c0), x);
+  uint32_t ui = *reinterpret_cast<const uint32_t*>(&u), ti;
+  asm("tanh.approx.f16x2 %0, %1;" : "=r"(ti) : "r"(ui));
+  const __half2 hx = __hmul2(x, __floats2half2_rn(0.5f, 0.5f));
+  const __half2 g = __hfma2(hx, *reinterpret_cast<const __half2*>(&ti), hx);
+  return *reinterpret_cast<const uint32_t*>(&g);
 }
 DSG_DEVINL void unpack8(const uint4 u, float* v) {
   const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&u);
@@ -200,7 +212,7 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
       Phases ph{(0xFu << B_ACCF)};                 // accumulators start free
       int slot = 0;
       const uint32_t xs_addr = smem_u32(smem + OFF_XS), buf_addr = smem_u32(smem + OFF_BUF), w_addr = smem_u32(smem + OFF_W);
-      constexpr uint32_t idesc128 = make_idesc_bf16(128, 128), idesc64 = make_idesc_bf16(128, 64);
+      constexpr uint32_t idesc128 = make_idesc_bf16(128, 128), idesc64 = make_idesc_bf16(128, 64), idesc128h = make_idesc_f16(128, 128);
       // one weight tile: 4 UMMAs (K = 64) of A k-tile `a_tile` against the current stage
       long long t_w = 0, t_o = 0;
       const bool prof = PROF && P.prof != nullptr && blockIdx.x == 0;
@@ -264,7 +276,7 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
               if (c == 0) { owait(B_ACCF + 0); owait(B_ACCF + 1); }
               tcgen05_fence_after();
               for (int nh = 0; nh < 2; ++nh)
-                for (int kb2 = 0; kb2 < 2; ++kb2) tile(buf_addr + ((c & 1) * 2 + kb2) * KT, nh * 128, idesc128, c > 0 || kb2 > 0);
+                for (int kb2 = 0; kb2 < 2; ++kb2) tile(buf_addr + ((c & 1) * 2 + kb2) * KT, nh * 128, idesc128h, c > 0 || kb2 > 0);
               tcgen05_commit(&bars[B_BUFF + (c & 1)]);
               if (c + 2 < 8) ff1(c + 2);
             }
@@ -313,6 +325,8 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
     __nv_bfloat16* Vs = reinterpret_cast<__nv_bfloat16*>(smem + OFF_V);
     float* red = reinterpret_cast<float*>(smem + OFF_RED);
     float* b1s = reinterpret_cast<float*>(smem + OFF_B1);
+    float* lnp = reinterpret_cast<float*>(smem + OFF_LNP);
+    float4* lnp4 = reinterpret_cast<float4*>(smem + OFF_LNP);
     uint8_t* XS = smem + OFF_XS;
     uint8_t* BUF = smem + OFF_BUF;
     float v[32];
@@ -341,7 +355,7 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
       tcgen05_fence_after();
       float sum = 0.f, sq = 0.f;
 #pragma unroll 1
-      for (int c4 = 0; c4 < 4; ++c4) {
+      for (int c4 = 0; c4 < (q4 < 3 ? 4 : 0); ++c4) {         // rows 96..127 carry no token (and hold the parameters)
         const int col0 = sub * 128 + c4 * 32;
         tmem_ld32(tlane + col0, v);
 #pragma unroll
@@ -363,13 +377,13 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
       const float mean = sum * (1.0f / D);
       const float rstd = rsqrtf(fmaxf(sq * (1.0f / D) - mean * mean, 0.f) + 1e-5f);
 #pragma unroll 1
-      for (int c4 = 0; c4 < 4; ++c4) {
+      for (int c4 = 0; c4 < (q4 < 3 ? 4 : 0); ++c4) {
         const int col0 = sub * 128 + c4 * 32;
         tmem_ld32(tlane + col0, v);
 #pragma unroll
         for (int i = 0; i < 32; i += 4) {
-          const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma + col0 + i));
-          const float4 b4 = __ldg(reinterpret_cast<const float4*>(beta + col0 + i));
+          const float4 g4 = *reinterpret_cast<const float4*>(gamma + col0 + i);          // shared memory (OFF_LNP)
+          const float4 b4 = *reinterpret_cast<const float4*>(beta + col0 + i);
           v[i] = (v[i] - mean) * rstd * g4.x + b4.x; v[i + 1] = (v[i + 1] - mean) * rstd * g4.y + b4.y;
           v[i + 2] = (v[i + 2] - mean) * rstd * g4.z + b4.z; v[i + 3] = (v[i + 3] - mean) * rstd * g4.w + b4.w;
         }
@@ -557,7 +571,14 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
           // With 225 KB of shared memory the L1 is a few KB: every parameter read is an L2 round trip.  The hottest one
           // (linear1's bias, read by 64 GELU epilogues per step) is staged in shared memory once per layer; the first
           // named barrier of the attention phase orders it before its first use.
-          reinterpret_cast<float4*>(b1s)[wt] = __ldg(reinterpret_cast<const float4*>(lp + P_B1) + wt);
+          {
+            const float4 t4 = __ldg(reinterpret_cast<const float4*>(lp + P_B1) + wt);
+            reinterpret_cast<__half2*>(b1s)[2 * wt] = __floats2half2_rn(t4.x, t4.y);
+            reinterpret_cast<__half2*>(b1s)[2 * wt + 1] = __floats2half2_rn(t4.z, t4.w);
+            // LayerNorm gains / biases -> the spare rows of XS (g1 | be1 are contiguous in lparams, so are g2 | be2)
+            const int which = wt >> 7, i4 = wt & 127;
+            lnp4[wt] = __ldg(reinterpret_cast<const float4*>(lp + (which ? P_G2 : P_G1)) + i4);
+          }
           if (wt < 64) {                                 // q bias (per head, [h][64]); the k bias drops out of the softmax,
             const int h = wt >> 4, i4 = wt & 15;        // the v bias is folded into bo' = bo + Wo bv at set-up
             reinterpret_cast<float4*>(b1s + 1024)[wt] = __ldg(reinterpret_cast<const float4*>(lp + P_BQKV + h * 192) + i4);
@@ -668,7 +689,7 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
             if (hb == 1 && lane == 0) mbar_arrive(&bars[B_BUFR + (h >> 1)]);
             lap(PF_W_ATT);
           }
-          layernorm_epilogue(b1s + 1280, lp + P_G1, lp + P_BE1);
+          layernorm_epilogue(b1s + 1280, lnp, lnp + 256);
           // ---- FFN: GELU epilogue per 128-unit chunk -> BUF half (c & 1) as the A operand of linear2
           for (int c = 0; c < 8; ++c) {
             const int qd = 2 + (c & 1);
@@ -684,19 +705,21 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
               tcgen05_fence_before();
               __syncwarp();
               if (lane == 0) mbar_arrive(&bars[B_ACCF + qd]);      // accumulator free: values are in registers now
-              const float* b1 = b1s + c * 128 + cc0;
+              // GELU in packed fp16 (tanh form on MUFU.TANH, 4 instructions per element): the hidden is stored as fp16, which
+              // keeps 3 more mantissa bits than the bf16 it replaces; |half-tanh GELU - exact| rms 5e-4 vs 2e-3 for bf16(exact)
+              if (q4 < 3) {
+                const __half2* b1h = reinterpret_cast<const __half2*>(b1s) + ((c * 128 + cc0) >> 1);
+                uint32_t ha[16], hb[16];
 #pragma unroll
-              for (int i = 0; i < 32; i += 4) {
-                const float4 ba = *reinterpret_cast<const float4*>(b1 + i), bb = *reinterpret_cast<const float4*>(b1 + 32 + i);
-                va[i] = gelu_fast(va[i] + ba.x); va[i + 1] = gelu_fast(va[i + 1] + ba.y);
-                va[i + 2] = gelu_fast(va[i + 2] + ba.z); va[i + 3] = gelu_fast(va[i + 3] + ba.w);
-                vb[i] = gelu_fast(vb[i] + bb.x); vb[i + 1] = gelu_fast(vb[i + 1] + bb.y);
-                vb[i + 2] = gelu_fast(vb[i + 2] + bb.z); vb[i + 3] = gelu_fast(vb[i + 3] + bb.w);
-              }
+                for (int i = 0; i < 16; ++i) {
+                  ha[i] = gelu_h2(__hadd2(__floats2half2_rn(va[2 * i], va[2 * i + 1]), b1h[i]));
+                  hb[i] = gelu_h2(__hadd2(__floats2half2_rn(vb[2 * i], vb[2 * i + 1]), b1h[16 + i]));
+                }
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                *reinterpret_cast<uint4*>(BUF + a_off(r, (c & 1) * 128 + cc0 + i * 8)) = pack8(va + i * 8);
-                *reinterpret_cast<uint4*>(BUF + a_off(r, (c & 1) * 128 + cc0 + 32 + i * 8)) = pack8(vb + i * 8);
+                for (int i = 0; i < 4; ++i) {
+                  *reinterpret_cast<uint4*>(BUF + a_off(r, (c & 1) * 128 + cc0 + i * 8)) = make_uint4(ha[4 * i], ha[4 * i + 1], ha[4 * i + 2], ha[4 * i + 3]);
+                  *reinterpret_cast<uint4*>(BUF + a_off(r, (c & 1) * 128 + cc0 + 32 + i * 8)) = make_uint4(hb[4 * i], hb[4 * i + 1], hb[4 * i + 2], hb[4 * i + 3]);
+                }
               }
             }
             fence_async_smem();
@@ -704,7 +727,7 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
             if (lane == 0) mbar_arrive(&bars[B_BUFR + (c & 1)]);
             lap(PF_W_GELU);
           }
-          layernorm_epilogue(b1s + 1536, lp + P_G2, lp + P_BE2);
+          layernorm_epilogue(b1s + 1536, lnp + 512, lnp + 768);
           debug_dump(l + 1, clip);
         }
 

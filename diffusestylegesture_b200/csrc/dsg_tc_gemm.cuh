@@ -139,6 +139,11 @@ DSG_DEVINL constexpr uint32_t make_idesc_bf16(int m, int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
+// same with A = B = fp16 (format code 0)
+DSG_DEVINL constexpr uint32_t make_idesc_f16(int m, int n) {
+  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
 template <int BN, int STAGES>
 struct TcSmem {
   static constexpr int A_BYTES = BM * BK * 2;

@@ -1,6 +1,7 @@
 // Helper kernels of the tensor-core path: operand packing, the pre-drawn noise tile, bf16 self-attention.
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include "dsg_common.cuh"
 
 // fp32 [rows, cols] (leading dim ld_src) -> bf16 [rows_pad, cols_pad], zero padding.
@@ -10,6 +11,15 @@ static __global__ void __launch_bounds__(256) pack_weight_bf16_kernel(const floa
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
     const int r = (int)(e / cols_pad), c = (int)(e - (long long)r * cols_pad);
     dst[e] = __float2bfloat16_rn((r < rows && c < cols) ? src[(long long)r * ld_src + c] : 0.f);
+  }
+}
+// same, IEEE half (the clip kernel runs linear2 on fp16 operands: 11-bit mantissa for the GELU'd hidden and for W2)
+static __global__ void __launch_bounds__(256) pack_weight_f16_kernel(const float* __restrict__ src, __half* __restrict__ dst,
+                                                             int rows, int cols, long long ld_src, int rows_pad, int cols_pad) {
+  const long long total = (long long)rows_pad * cols_pad;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(e / cols_pad), c = (int)(e - (long long)r * cols_pad);
+    dst[e] = __float2half_rn((r < rows && c < cols) ? src[(long long)r * ld_src + c] : 0.f);
   }
 }
 

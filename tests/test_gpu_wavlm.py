@@ -57,7 +57,7 @@ def test_wav_to_bvh_through_both_engines(tmp_path):
                               SG_filter=True, minibatch=True, style=[1, 0, 0, 0, 0, 0], seed=7, save_dir=str(tmp_path))
     assert poses.shape == (160 - 8, 1141) and np.isfinite(poses).all()
     lines = open(path).read().splitlines()
-    assert lines[0] == "HIERARCHY" and any(l.startswith("Frames: 152") for l in lines)
+    assert lines[0] == "HIERARCHY" and any(l.startswith("Frames: 456") for l in lines)      # 152 frames at 20 fps -> 60 fps
     # batched conditioning == per-segment conditioning (reference loop order, sample.py:238-251)
     a = torch.from_numpy(audio[:160 * 800]).reshape(2, 64000)
     w0 = torch.cat((torch.zeros(6400), a[0]))[None]
