@@ -35,12 +35,19 @@ constexpr int OFF_V = OFF_K + 96 * QLD * 2;
 constexpr int OFF_RED = OFF_V + 96 * QLD * 2;
 constexpr int OFF_B1 = OFF_RED + 2048;           // per-layer parameters staged in shared memory: b1[1024] fp16 | 2 KB spare | fp32 bq[256] | bo'[256] | b2[256]
 constexpr int OFF_LNP = OFF_XS + 12288;          // rows 96..127 of XS k-tile 0 (never a token): fp32 g1[256] | be1[256] | g2[256] | be2[256]
+constexpr int OFF_BOUT0 = OFF_XS + KT + 12288;   // same rows of k-tile 1: pose-head bias [0, 1024); k-tile 2: [1024, 1152)
+constexpr int OFF_BOUT1 = OFF_XS + 2 * KT + 12288;
+// pose-head phase: x_t / z chunks of 32 joint channels ([32][88] fp32 = 11,264 B each) are bulk-copied into 4 slots carved out
+// of BUF and the (idle) attention staging area
+constexpr int HCH = 32, HBYTES = HCH * T * 4, NHS = 4, NCHUNK = JPAD / HCH;
+constexpr int XA_BYTES = (JPAD / 64) * KT;       // per clip: x_t as bf16 A-operand k-blocks [18][128 x 64], SWIZZLE_128B image
 constexpr int OFF_BAR = OFF_B1 + 4096 + 3072;
 constexpr int SMEM_BYTES = OFF_BAR + 512 + 1024;
 constexpr int ZLD = 264;                    // rope'd h staging row stride (bf16), lives in BUF: 104 rows x 528 B
 constexpr int ZROWS = 104;
 static_assert(ZROWS * ZLD * 2 <= 4 * KT, "Z staging must fit in BUF");
 static_assert(SMEM_BYTES <= 232448, "shared memory budget");
+static_assert(5 * HBYTES <= 4 * KT && 3 * HBYTES <= 3 * 96 * QLD * 2, "pose-head slots");
 
 // per-layer fp32 parameter block (biases, LayerNorm): offsets in floats
 constexpr int P_BQKV = 0, P_BO = 768, P_G1 = 1024, P_BE1 = 1280, P_B1 = 1536, P_B2 = 2560, P_G2 = 2816, P_BE2 = 3072, P_SIZE = 3328;
@@ -49,10 +56,11 @@ constexpr int R_LAYER = 2048, R_QKV = 0, R_WO = 768, R_W1 = 1024, R_HEAD = NL * 
 
 // barrier indices
 enum { B_WFULL = 0, B_WEMPTY = 3, B_AFULL = 6, B_AEMPTY = 10, B_ACCR = 14, B_ACCF = 18, B_XSR = 22, B_BUFR = 23, B_BUFF = 25,
-       B_ZR = 27, B_ZF = 28, B_COUNT = 29 };
+       B_ZR = 27, B_ZF = 28, B_HFULL = 29, B_HEMPTY = 33, B_HGO = 37, B_XAR = 38, B_COUNT = 39 };
 
 struct ClipParams {
   float* x;                 // [B][J][T] fp32, in/out
+  uint8_t* xa;              // [B][XA_BYTES]: bf16(x_t) as the input GEMM's A k-blocks (written by pack_xa_kernel, then by the head epilogue)
   float* z;                 // [B][J*T] fp32 noise scratch
   const float* cond;        // [B][T][D]
   const float* emb1;        // [B][D]
@@ -118,9 +126,32 @@ DSG_DEVINL void tie32(float* v) {
 }
 
 struct Phases {            // one phase bit per barrier, toggled on every completed wait
-  uint32_t bits;
-  DSG_DEVINL void wait(uint64_t* bars, int id) { mbar_wait(&bars[id], (bits >> id) & 1u); bits ^= 1u << id; }
+  uint64_t bits;
+  DSG_DEVINL void wait(uint64_t* bars, int id) { mbar_wait(&bars[id], (uint32_t)(bits >> id) & 1u); bits ^= 1ull << id; }
 };
+DSG_DEVINL void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+DSG_DEVINL void fence_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// byte offsets of head slot s: x_t chunk, z chunk
+DSG_DEVINL int hslot_x(int s) { return s == 0 ? OFF_BUF : (s == 1 ? OFF_BUF + 2 * HBYTES : (s == 2 ? OFF_Q : OFF_BUF + 4 * HBYTES)); }
+DSG_DEVINL int hslot_z(int s) { return s == 0 ? OFF_BUF + HBYTES : (s == 1 ? OFF_BUF + 3 * HBYTES : (s == 2 ? OFF_Q + HBYTES : OFF_Q + 2 * HBYTES)); }
+
+// x fp32 [B][J][T] -> xa (the clip kernel's A k-blocks): row = frame + 1, column = joint channel, bf16, SWIZZLE_128B image.
+// Rows 0 and 89..127 and the columns >= J stay zero (the buffer is allocated zeroed and never written there).
+static __global__ void __launch_bounds__(256) pack_xa_kernel(const float* __restrict__ x, uint8_t* __restrict__ xa) {
+  const int kb = blockIdx.x, clip = blockIdx.y;
+  const float* xc = x + (long long)clip * J * T;
+  uint8_t* at = xa + (long long)clip * XA_BYTES + (long long)kb * KT;
+  for (int it = threadIdx.x; it < 32 * T; it += 256) {
+    const int pr = it / T, f = it - pr * T;
+    const int j = kb * 64 + 2 * pr;
+    const float lo = (j < J) ? xc[(long long)j * T + f] : 0.f, hi = (j + 1 < J) ? xc[(long long)(j + 1) * T + f] : 0.f;
+    const int rr = f + 1, cc = 2 * pr;
+    *reinterpret_cast<uint32_t*>(at + (rr >> 3) * 1024 + (rr & 7) * 128 + (((cc >> 3) ^ (rr & 7)) << 4) + (cc & 7) * 2) = pack_bf16x2(lo, hi);
+  }
+}
 
 // ---------------------------------------------------------------------------------------------------
 template <bool PROF>
@@ -139,12 +170,14 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
   if (threadIdx.x == 0) {
     for (int i = 0; i < NS; ++i) { mbar_init(&bars[B_WFULL + i], 1); mbar_init(&bars[B_WEMPTY + i], 1); }
     for (int i = 0; i < 4; ++i) {
-      mbar_init(&bars[B_AFULL + i], 8); mbar_init(&bars[B_AEMPTY + i], 1);
+      mbar_init(&bars[B_AFULL + i], 1); mbar_init(&bars[B_AEMPTY + i], 1);
+      mbar_init(&bars[B_HFULL + i], 1); mbar_init(&bars[B_HEMPTY + i], 8);
       mbar_init(&bars[B_ACCR + i], 1);  mbar_init(&bars[B_ACCF + i], 8);
     }
     mbar_init(&bars[B_XSR], 8);
     for (int i = 0; i < 2; ++i) { mbar_init(&bars[B_BUFR + i], 8); mbar_init(&bars[B_BUFF + i], 1); }
     mbar_init(&bars[B_ZR], 2); mbar_init(&bars[B_ZF], 8);
+    mbar_init(&bars[B_HGO], 1); mbar_init(&bars[B_XAR], 8);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_in) : "memory");
@@ -170,7 +203,7 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
   if (warp == 0) {
     // =================================================== TMA weight producer ===================================================
     if (lane == 0) {
-      Phases ph{0x7u << B_WEMPTY};                 // "empty" barriers start free
+      Phases ph{(0x7ull << B_WEMPTY) | (0xFull << B_AEMPTY) | (0xFull << B_HEMPTY)};     // "empty" barriers start free
       int slot = 0;
       long long t_wait = 0;
       const bool prof = PROF && P.prof != nullptr && blockIdx.x == 0;
@@ -182,10 +215,23 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
         tma_load_2d(smem + OFF_W + slot * WSTAGE, m, &bars[B_WFULL + slot], kcol, row);
         slot = (slot + 1 == NS) ? 0 : slot + 1;
       };
+      bool first = true;
       for (int clip = blockIdx.x; clip < P.B; clip += gridDim.x)
         for (int k = 0; k < P.n_run; ++k) {
-          for (int kb = 0; kb < JPAD / 64; ++kb)
+          const int index = first_index - k;
+          const bool nz = (index != 0) && (P.sampler == 0);
+          // x_t as bf16 A k-blocks: written by pack_xa_kernel before the launch, afterwards by the head epilogue of the previous
+          // step (B_XAR: those stores are complete and fenced for the async proxy, and BUF is no longer read)
+          if (!first) ph.wait(bars, B_XAR);
+          first = false;
+          const uint8_t* xa = P.xa + (long long)clip * XA_BYTES;
+          for (int kb = 0; kb < JPAD / 64; ++kb) {
+            const int sl = kb & 3;
+            ph.wait(bars, B_AEMPTY + sl);
+            mbar_expect_tx(&bars[B_AFULL + sl], KT);
+            bulk_load(smem + OFF_BUF + sl * KT, xa + (long long)kb * KT, KT, &bars[B_AFULL + sl]);
             for (int nh = 0; nh < 2; ++nh) load(&tm_in, nh * 128, kb * 64, WSTAGE);
+          }
           for (int l = 0; l < NL; ++l) {
             const int rb = l * R_LAYER;
             for (int h = 0; h < NH; ++h)
@@ -201,15 +247,32 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
               if (c + 2 < 8) ff1(c + 2);
             }
           }
-          for (int t = 0; t < JPAD / 128; ++t)
+          // pose head: weights + the x_t / z chunks the posterior needs (BUF is free once the last linear2 has completed)
+          for (int kb = 0; kb < 4; ++kb) load(&tm_w128, R_HEAD, kb * 64, WSTAGE);
+          ph.wait(bars, B_HGO);
+          if (nz) ph.wait(bars, B_ZR);
+          const float* xc = P.x + (long long)clip * J * T;
+          const float* zc = P.z + (long long)clip * J * T;
+          auto hload = [&](int c) {
+            const int sl = c & 3, j0 = c * HCH;
+            const uint32_t bytes = (uint32_t)((J - j0 < HCH ? J - j0 : HCH) * T * 4);
+            ph.wait(bars, B_HEMPTY + sl);
+            mbar_expect_tx(&bars[B_HFULL + sl], nz ? 2 * bytes : bytes);
+            bulk_load(smem + hslot_x(sl), xc + (long long)j0 * T, bytes, &bars[B_HFULL + sl]);
+            if (nz) bulk_load(smem + hslot_z(sl), zc + (long long)j0 * T, bytes, &bars[B_HFULL + sl]);
+          };
+          for (int c = 0; c < NHS; ++c) hload(c);
+          for (int t = 1; t < JPAD / 128; ++t) {
             for (int kb = 0; kb < 4; ++kb) load(&tm_w128, R_HEAD + t * 128, kb * 64, WSTAGE);
+            for (int c = 4 * t; c < 4 * t + 4; ++c) hload(c);
+          }
         }
       if (prof) P.prof[PF_PROD_WAIT_EMPTY] = t_wait;
     }
   } else if (warp == 1) {
     // =================================================== MMA issuer ===================================================
     if (lane == 0) {
-      Phases ph{(0xFu << B_ACCF)};                 // accumulators start free
+      Phases ph{(0xFull << B_ACCF)};               // accumulators start free
       int slot = 0;
       const uint32_t xs_addr = smem_u32(smem + OFF_XS), buf_addr = smem_u32(smem + OFF_BUF), w_addr = smem_u32(smem + OFF_W);
       constexpr uint32_t idesc128 = make_idesc_bf16(128, 128), idesc64 = make_idesc_bf16(128, 64), idesc128h = make_idesc_f16(128, 128);
@@ -281,6 +344,7 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
               if (c + 2 < 8) ff1(c + 2);
             }
             tcgen05_commit(&bars[B_ACCR + 0]); tcgen05_commit(&bars[B_ACCR + 1]);
+            if (l == NL - 1) tcgen05_commit(&bars[B_HGO]);      // every read of BUF by the tensor core is complete
           }
           // ---- pose head: 9 tiles of 128 joint channels, D rotates over the 4 quarters
           owait(B_XSR);
@@ -296,7 +360,7 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
     }
   } else if (warp < 4) {
     // =================================================== noise pre-draw ===================================================
-    Phases ph{1u << B_ZF};
+    Phases ph{1ull << B_ZF};
     const int nt = (warp - 2) * 32 + lane;           // 0..63
     for (int clip = blockIdx.x; clip < P.B; clip += gridDim.x) {
       const uint32_t cid = (uint32_t)P.clip_ids[clip];
@@ -307,6 +371,7 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
         ph.wait(bars, B_ZF);
         for (int q = nt; q < J * T / 4; q += 64)
           *reinterpret_cast<float4*>(zc + 4 * q) = philox_normal4((uint32_t)q, (uint32_t)(1 + k), cid, segment, key0, key1);
+        fence_async_all();                               // z is read back through the async proxy (bulk copies)
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars[B_ZR]);
       }
@@ -318,7 +383,7 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
     const int r = q4 * 32 + lane;                    // accumulator row == token slot s (row 0 = token, rows 1..88 = frames)
     const int wt = threadIdx.x - 128;                // 0..255
     const uint32_t tlane = tmem + ((uint32_t)(q4 * 32) << 16);
-    Phases ph{(0xFu << B_AEMPTY) | (0x3u << B_BUFF)};
+    Phases ph{(0x3ull << B_BUFF)};
     __nv_bfloat16* Zs = reinterpret_cast<__nv_bfloat16*>(smem + OFF_BUF);
     __nv_bfloat16* Qs = reinterpret_cast<__nv_bfloat16*>(smem + OFF_Q);
     __nv_bfloat16* Ks = reinterpret_cast<__nv_bfloat16*>(smem + OFF_K);
@@ -407,46 +472,27 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
       }
     };
 
+    for (int i = wt; i < JPAD; i += 256)               // pose-head bias -> token-less rows of XS k-tiles 1 and 2
+      *reinterpret_cast<float*>(smem + (i < 1024 ? OFF_BOUT0 + i * 4 : OFF_BOUT1 + (i - 1024) * 4)) = __ldg(P.bout + i);
     for (int clip = blockIdx.x; clip < P.B; clip += gridDim.x) {
       float* xc = P.x + (long long)clip * J * T;
-      const float* zc = P.z + (long long)clip * J * T;
+      uint8_t* xac = P.xa + (long long)clip * XA_BYTES;
       const float* condc = P.cond + (long long)clip * T * D;
       for (int k = 0; k < P.n_run; ++k) {
         const int index = first_index - k;
         const int trow = P.tmap[index];
         const bool nz = (index != 0) && (P.sampler == 0);
-        // ---------------- stage the A operand of the input GEMM: x_t [J][T] fp32 -> bf16 k-blocks [frame+1][64 channels]
+        // (the A operand of the input GEMM is bulk-copied by the producer warp from the bf16 k-block image of x_t)
         ph.wait(bars, B_BUFF + 0); ph.wait(bars, B_BUFF + 1);
-        for (int kb = 0; kb < JPAD / 64; ++kb) {
-          const int sl = kb & 3;
-          ph.wait(bars, B_AEMPTY + sl);
-          uint8_t* at = BUF + sl * KT;
-          float lo[11], hi[11];
-#pragma unroll
-          for (int m = 0; m < 11; ++m) {
-            const int it = wt + 256 * m;                 // 0..2815 = 32 channel pairs x 88 frames
-            const int pr = it / T, f = it - pr * T;
-            const int j = kb * 64 + 2 * pr;
-            lo[m] = (j < J) ? xc[(long long)j * T + f] : 0.f;      // plain loads: x is rewritten by this CTA every step
-            hi[m] = (j + 1 < J) ? xc[(long long)(j + 1) * T + f] : 0.f;
-          }
-#pragma unroll
-          for (int m = 0; m < 11; ++m) {
-            const int it = wt + 256 * m;
-            const int pr = it / T, f = it - pr * T;
-            const int rr = f + 1, cc = 2 * pr;
-            *reinterpret_cast<uint32_t*>(at + (rr >> 3) * 1024 + (rr & 7) * 128 + (((cc >> 3) ^ (rr & 7)) << 4) + (cc & 7) * 2) =
-                pack_bf16x2(lo[m], hi[m]);
-          }
-          fence_async_smem();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&bars[B_AFULL + sl]);
-        }
         lap(PF_W_STAGE);
         // ---------------- input epilogue: + cond + TW[t], rotary (position = frame), bf16 -> Z staging (in BUF)
         ph.wait(bars, B_ACCR + 0); ph.wait(bars, B_ACCR + 1);
         lap(PF_W_IN_WAIT);
         tcgen05_fence_after();
+        // BUF held x_t / z chunks and A k-blocks since the last step: the pad rows of the Z staging (read as V with zero weight
+        // by the last windows) must be finite
+        for (int i = wt; i < (ZROWS - T) * 33; i += 256)
+          reinterpret_cast<uint4*>(Zs + (T + i / 33) * ZLD)[i % 33] = make_uint4(0u, 0u, 0u, 0u);
         {
           const int f = r - 1;
           const bool ok = r >= 1 && r <= T;
@@ -731,43 +777,50 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
           debug_dump(l + 1, clip);
         }
 
-        // ---------------- pose head + posterior: x <- f(x0, x, z) in place, coalesced along frames
-        if (nz) ph.wait(bars, B_ZR);
+        // ---------------- pose head + posterior: x <- f(x0, x, z) in place (fp32, global) and as next step's bf16 A k-blocks.
+        // Chunk c = 32 joint channels (TMEM quarter (c >> 2) & 3, columns (c & 3) * 32); the two column halves take 16 each.
         lap(PF_W_ZWAIT);
         {
           const float4 cf = P.coef[index];
           const int f = r - 1;
           const bool ok = r >= 1 && r <= T;
-          for (int t = 0; t < JPAD / 128; ++t) {
-            ph.wait(bars, B_ACCR + (t & 3));
+          for (int c = 0; c < NCHUNK; ++c) {
+            const int t = c >> 2, sl = c & 3;
+            if (sl == 0) ph.wait(bars, B_ACCR + (t & 3));
+            ph.wait(bars, B_HFULL + sl);
             lap(PF_W_HEAD_WAIT);
             tcgen05_fence_after();
-#pragma unroll 1
-            for (int ci = 0; ci < 2; ++ci) {
-              const int j0 = t * 128 + sub * 64 + ci * 32;
-              tmem_ld32(tlane + (t & 3) * 128 + sub * 64 + ci * 32, v);
-              if (!ok || j0 >= J) continue;
-              const long long base = (long long)j0 * T + f;
-              float xt[32], zz[32];
+            const int j0 = c * HCH + sub * 16;
+            float v16[16];
+            tmem_ld16_issue(tlane + (t & 3) * 128 + sl * 32 + sub * 16, v16);
+            tmem_ld_wait();
+            if (ok && j0 < J) {
+              const float* xs = reinterpret_cast<const float*>(smem + hslot_x(sl)) + sub * 16 * T + f;
+              const float* zs = reinterpret_cast<const float*>(smem + hslot_z(sl)) + sub * 16 * T + f;
+              const float* bo = reinterpret_cast<const float*>(smem + (j0 < 1024 ? OFF_BOUT0 + j0 * 4 : OFF_BOUT1 + (j0 - 1024) * 4));
+              float* xg = xc + (long long)j0 * T + f;
 #pragma unroll
-              for (int i = 0; i < 32; ++i) xt[i] = (j0 + i < J) ? xc[base + (long long)i * T] : 0.f;
-#pragma unroll
-              for (int i = 0; i < 32; ++i) zz[i] = (nz && j0 + i < J) ? zc[base + (long long)i * T] : 0.f;
-#pragma unroll
-              for (int i = 0; i < 32; ++i) {
-                const float x0 = v[i] + __ldg(P.bout + j0 + i);
-                v[i] = posterior_apply(P.sampler, cf, x0, xt[i], zz[i], nz);
+              for (int i = 0; i < 16; ++i) {
+                const bool in = j0 + i < J;
+                const float xt = in ? xs[i * T] : 0.f, zz = (nz && in) ? zs[i * T] : 0.f;
+                const float x0 = v16[i] + bo[i];
+                v16[i] = in ? posterior_apply(P.sampler, cf, x0, xt, zz, nz) : 0.f;
+                if (in) xg[(long long)i * T] = v16[i];
               }
-#pragma unroll
-              for (int i = 0; i < 32; ++i) if (j0 + i < J) xc[base + (long long)i * T] = v[i];
+              uint8_t* row = xac + (long long)(j0 >> 6) * KT + (r >> 3) * 1024 + (r & 7) * 128;
+              const int c8 = (j0 & 63) >> 3;
+              *reinterpret_cast<uint4*>(row + (((c8) ^ (r & 7)) << 4)) = pack8(v16);
+              *reinterpret_cast<uint4*>(row + (((c8 + 1) ^ (r & 7)) << 4)) = pack8(v16 + 8);
             }
-            release_acc(t & 3, -1, false, -1);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars[B_HEMPTY + sl]);
+            if (sl == 3) release_acc(t & 3, -1, false, -1);
             lap(PF_W_HEAD);
           }
         }
+        fence_async_all();                               // x and its k-block image are read back by bulk copies (async proxy)
         __syncwarp();
-        if (nz && lane == 0) mbar_arrive(&bars[B_ZF]);
-        workers_sync();                                  // x_{t-1} of every frame is visible to the staging loop of the next step
+        if (lane == 0) { mbar_arrive(&bars[B_XAR]); if (nz) mbar_arrive(&bars[B_ZF]); }
       }
     }
     if constexpr (PROF) { if (prof) for (int i = PF_W_STAGE; i < PF_COUNT; ++i) P.prof[i] = pf[i]; }

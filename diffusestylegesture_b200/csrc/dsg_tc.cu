@@ -38,6 +38,7 @@ struct dsg_tc_state {
   bool clip_ok = false;
   bf16 *wK256 = nullptr, *wK1024 = nullptr;
   float *lparams = nullptr, *bout = nullptr;
+  uint8_t* xa = nullptr;
   long long* prof = nullptr;
   CUtensorMap tm_cin, tm_c128, tm_c64, tm_cw2;
 };
@@ -91,6 +92,7 @@ static int clip_setup(dsg_engine* e) {
   CUDA_TRY(cudaMemcpy(t->lparams, lp.data(), lp.size() * sizeof(float), cudaMemcpyHostToDevice));
   TRY(dalloc0(&t->bout, (size_t)JPAD));
   TRY(dalloc0(&t->prof, (size_t)64));
+  TRY(dalloc0(&t->xa, (size_t)d.max_batch * XA_BYTES));
   CUDA_TRY(cudaMemcpy(t->bout, e->w[W_OUT_B], (size_t)J * sizeof(float), cudaMemcpyDeviceToDevice));
   TRY(make_tmap(&t->tm_cin, t->Wxp, D, JPAD, 128));
   TRY(make_tmap(&t->tm_c128, t->wK256, rows256, D, 128));
@@ -106,12 +108,14 @@ static int clip_run(dsg_engine* e, int B, float* xd, int n_run, int first_index,
   dsg_tc_state* t = e->tc;
   TRY(dsg_upload_loop_params(e, first_index, seed, segment, st));
   clip::ClipParams p;
-  p.x = xd; p.z = t->z; p.cond = e->cond; p.emb1 = e->emb1; p.te = e->te; p.TW = e->TW; p.cs = e->cs_local;
+  p.x = xd; p.xa = t->xa; p.z = t->z; p.cond = e->cond; p.emb1 = e->emb1; p.te = e->te; p.TW = e->TW; p.cs = e->cs_local;
   p.lparams = t->lparams; p.bout = t->bout; p.coef = e->coef; p.tmap = e->tmap; p.clip_ids = e->clip_ids; p.lp = e->d_loop;
   p.B = B; p.n_run = n_run; p.sampler = e->sampler;
   p.prof = getenv("DSG_CLIP_PROF") ? t->prof : nullptr;
   p.dbg = e->dbg; p.dbg_slot = (long long)e->d.max_batch * e->S * e->d.latent_dim; p.debug = e->debug ? 1 : 0;
   const int grid = B < e->num_sms ? B : e->num_sms;
+  clip::pack_xa_kernel<<<dim3(clip::JPAD / 64, B), 256, 0, st>>>(xd, t->xa);       // x_T as the first step's A k-blocks
+  e->launches++;
   if (p.prof) clip::clip_kernel<true><<<grid, 384, clip::SMEM_BYTES, st>>>(t->tm_cin, t->tm_c128, t->tm_c64, t->tm_cw2, p);
   else clip::clip_kernel<false><<<grid, 384, clip::SMEM_BYTES, st>>>(t->tm_cin, t->tm_c128, t->tm_c64, t->tm_cw2, p);
   e->launches++;
@@ -180,7 +184,7 @@ void dsg_tc_destroy(dsg_engine* e) {
   dsg_tc_state* t = e->tc;
   if (!t) return;
   if (t->exec) cudaGraphExecDestroy(t->exec);
-  void* ptrs[] = {t->Wxp, t->Wout, t->xb, t->xsb, t->qkvb, t->attb, t->ffb, t->hS, t->z, t->xloop, t->wK256, t->wK1024, t->lparams, t->bout, t->prof};
+  void* ptrs[] = {t->Wxp, t->Wout, t->xb, t->xsb, t->qkvb, t->attb, t->ffb, t->hS, t->z, t->xloop, t->wK256, t->wK1024, t->lparams, t->bout, t->prof, t->xa};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (auto& v : {t->Wqkv, t->Wo, t->W1, t->W2}) for (bf16* p : v) if (p) cudaFree(p);
   if (t->main) cudaStreamDestroy(t->main);
