@@ -4,8 +4,10 @@
 // all: no kernel boundaries, no grid barriers, no activation traffic through L2.  ZEGGS geometry (D 256, F 1024,
 // 4 x 64 global heads, 8 x 32 local heads, window 11, T 88, J 1141) is compiled in.
 //
-// Warp roles (384 threads):  0 = TMA weight producer   1 = tcgen05.mma issuer   2,3 = noise pre-draw (Philox)
-//                            4..11 = 8 worker warps: A-operand staging, all epilogues, both attentions.
+// Warp roles (512 threads, warp = 4 * sub + q4; q4 = TMEM lane quarter = scheduler):
+//   q4 == 3 (rows 96..127 carry no token): 3 = TMA producer (weights, x_t k-blocks, x_t / z chunks)   7 = tcgen05.mma issuer
+//                                          11, 15 = noise pre-draw (Philox)
+//   q4 <  3: 12 worker warps (4 per scheduler): all epilogues, both attentions; sub = column quarter of an epilogue.
 // Tensor memory (512 columns) = 4 quarters of 128 fp32 columns (Q0..Q3), handed back and forth per op with
 // ready/free mbarriers.  Shared memory:
 //   XS  [128 x 256] bf16, UMMA K-major SWIZZLE_128B (4 k-tiles)  — the residual stream AND the A operand; rows 96..127
@@ -82,7 +84,24 @@ DSG_DEVINL void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 DSG_DEVINL void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-DSG_DEVINL void workers_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+constexpr int NW = 12, NWT = NW * 32;          // worker warps / threads
+DSG_DEVINL void workers_sync() { asm volatile("bar.sync 1, 384;" ::: "memory"); }
+DSG_DEVINL void pair_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+DSG_DEVINL void tmem_ld8_issue(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr));
+}
+DSG_DEVINL void tmem_ld4_issue(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];\n" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr));
+}
+DSG_DEVINL void tmem_st4(uint32_t taddr, const float* v) {
+  const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]) : "memory");
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+DSG_DEVINL void tie4(float* v) { asm volatile("" : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]) :: "memory"); }
 DSG_DEVINL void ldsm_x2(uint32_t& r0, uint32_t& r1, const void* p) {
   const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
   asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(a));
@@ -155,7 +174,7 @@ static __global__ void __launch_bounds__(256) pack_xa_kernel(const float* __rest
 
 // ---------------------------------------------------------------------------------------------------
 template <bool PROF>
-__global__ void __launch_bounds__(384, 1)
+__global__ void __launch_bounds__(512, 1)
 clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152]   box 128 x 64
             const __grid_constant__ CUtensorMap tm_w128,   // K=256 slab          box 128 x 64
             const __grid_constant__ CUtensorMap tm_w64,    // K=256 slab          box  64 x 64
@@ -171,13 +190,13 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
     for (int i = 0; i < NS; ++i) { mbar_init(&bars[B_WFULL + i], 1); mbar_init(&bars[B_WEMPTY + i], 1); }
     for (int i = 0; i < 4; ++i) {
       mbar_init(&bars[B_AFULL + i], 1); mbar_init(&bars[B_AEMPTY + i], 1);
-      mbar_init(&bars[B_HFULL + i], 1); mbar_init(&bars[B_HEMPTY + i], 8);
-      mbar_init(&bars[B_ACCR + i], 1);  mbar_init(&bars[B_ACCF + i], 8);
+      mbar_init(&bars[B_HFULL + i], 1); mbar_init(&bars[B_HEMPTY + i], NW);
+      mbar_init(&bars[B_ACCR + i], 1);  mbar_init(&bars[B_ACCF + i], NW);
     }
-    mbar_init(&bars[B_XSR], 8);
-    for (int i = 0; i < 2; ++i) { mbar_init(&bars[B_BUFR + i], 8); mbar_init(&bars[B_BUFF + i], 1); }
-    mbar_init(&bars[B_ZR], 2); mbar_init(&bars[B_ZF], 8);
-    mbar_init(&bars[B_HGO], 1); mbar_init(&bars[B_XAR], 8);
+    mbar_init(&bars[B_XSR], NW);
+    for (int i = 0; i < 2; ++i) { mbar_init(&bars[B_BUFR + i], NW); mbar_init(&bars[B_BUFF + i], 1); }
+    mbar_init(&bars[B_ZR], 2); mbar_init(&bars[B_ZF], NW);
+    mbar_init(&bars[B_HGO], 1); mbar_init(&bars[B_XAR], NW);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_in) : "memory");
@@ -188,7 +207,7 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
   // zero the operand buffers once: rows that are never written (token slot of the A ring, rows >= S, Z pad rows) stay finite
   for (int i = threadIdx.x; i < (OFF_W) / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
   for (int i = threadIdx.x; i < (OFF_RED - OFF_Q) / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem + OFF_Q)[i] = make_uint4(0u, 0u, 0u, 0u);
-  if (warp == 1) {
+  if (warp == 7) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -200,7 +219,8 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
   const int first_index = P.lp->first_index;
   const uint32_t key0 = P.lp->key0, key1 = P.lp->key1, segment = P.lp->segment;
 
-  if (warp == 0) {
+  const int q4 = warp & 3, sub = warp >> 2;
+  if (q4 == 3 && sub == 0) {
     // =================================================== TMA weight producer ===================================================
     if (lane == 0) {
       Phases ph{(0x7ull << B_WEMPTY) | (0xFull << B_AEMPTY) | (0xFull << B_HEMPTY)};     // "empty" barriers start free
@@ -269,7 +289,7 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
         }
       if (prof) P.prof[PF_PROD_WAIT_EMPTY] = t_wait;
     }
-  } else if (warp == 1) {
+  } else if (q4 == 3 && sub == 1) {
     // =================================================== MMA issuer ===================================================
     if (lane == 0) {
       Phases ph{(0xFull << B_ACCF)};               // accumulators start free
@@ -358,10 +378,10 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
         }
       if (prof) { P.prof[PF_TOTAL] = clock64() - t_begin; P.prof[PF_MMA_WAIT_W] = t_w; P.prof[PF_MMA_WAIT_OTHER] = t_o; }
     }
-  } else if (warp < 4) {
+  } else if (q4 == 3) {
     // =================================================== noise pre-draw ===================================================
     Phases ph{1ull << B_ZF};
-    const int nt = (warp - 2) * 32 + lane;           // 0..63
+    const int nt = (sub - 2) * 32 + lane;            // 0..63
     for (int clip = blockIdx.x; clip < P.B; clip += gridDim.x) {
       const uint32_t cid = (uint32_t)P.clip_ids[clip];
       float* zc = P.z + (long long)clip * J * T;
@@ -378,23 +398,23 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
     }
   } else {
     // =================================================== workers ===================================================
-    const int ww = warp - 4;                         // 0..7
-    const int q4 = ww & 3, sub = ww >> 2;            // TMEM lane quarter (== warp % 4), column half
-    const int r = q4 * 32 + lane;                    // accumulator row == token slot s (row 0 = token, rows 1..88 = frames)
-    const int wt = threadIdx.x - 128;                // 0..255
+    // warp = 4 * sub + q4: q4 = TMEM lane quarter (rows 32 q4 .. +31; quarter 3 carries no token and hosts the service
+    // warps), sub = column quarter of every epilogue.  Three schedulers x four worker warps each.
+    const int wl = sub * 3 + q4;                     // 0..11
+    const int r = q4 * 32 + lane;                    // accumulator row == token slot s (row 0 = token, rows 1..88 = frames), 0..95
+    const int wt = wl * 32 + lane;                   // 0..383
     const uint32_t tlane = tmem + ((uint32_t)(q4 * 32) << 16);
     Phases ph{(0x3ull << B_BUFF)};
     __nv_bfloat16* Zs = reinterpret_cast<__nv_bfloat16*>(smem + OFF_BUF);
     __nv_bfloat16* Qs = reinterpret_cast<__nv_bfloat16*>(smem + OFF_Q);
     __nv_bfloat16* Ks = reinterpret_cast<__nv_bfloat16*>(smem + OFF_K);
     __nv_bfloat16* Vs = reinterpret_cast<__nv_bfloat16*>(smem + OFF_V);
-    float* red = reinterpret_cast<float*>(smem + OFF_RED);
+    float* red_s = reinterpret_cast<float*>(smem + OFF_RED);            // [4][96] row sums
+    float* red_q = reinterpret_cast<float*>(smem + OFF_B1 + 2048);      // [4][96] row sums of squares
     float* b1s = reinterpret_cast<float*>(smem + OFF_B1);
     float* lnp = reinterpret_cast<float*>(smem + OFF_LNP);
-    float4* lnp4 = reinterpret_cast<float4*>(smem + OFF_LNP);
     uint8_t* XS = smem + OFF_XS;
     uint8_t* BUF = smem + OFF_BUF;
-    float v[32];
     const bool prof = PROF && P.prof != nullptr && blockIdx.x == 0 && wt == 0;
     long long pf[PROF ? PF_COUNT : 1];
 #pragma unroll
@@ -413,66 +433,66 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
         if (buf_ready >= 0) mbar_arrive(&bars[B_BUFR + buf_ready]);
       }
     };
-    // residual + bias + LayerNorm on the accumulator in Q0|Q1, result -> XS (bf16).  Thread = (row, 128-column half).
+    // residual + bias + LayerNorm on the accumulator in Q0|Q1, result -> XS (bf16).  Thread = (row, 64-column quarter): the
+    // row's 64 values stay in registers across the one barrier that exchanges the partial sums.
     auto layernorm_epilogue = [&](const float* bias, const float* gamma, const float* beta) {
       ph.wait(bars, B_ACCR + 0); ph.wait(bars, B_ACCR + 1);
       lap(PF_W_LN_WAIT);
       tcgen05_fence_after();
+      float v[64];
+      const int col0 = sub * 64;
+      tmem_ld32_issue(tlane + col0, v); tmem_ld32_issue(tlane + col0 + 32, v + 32);
+      tmem_ld_wait(); tie32(v); tie32(v + 32);
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) { mbar_arrive(&bars[B_ACCF + 0]); mbar_arrive(&bars[B_ACCF + 1]); }     // the accumulator is in registers
       float sum = 0.f, sq = 0.f;
-#pragma unroll 1
-      for (int c4 = 0; c4 < (q4 < 3 ? 4 : 0); ++c4) {         // rows 96..127 carry no token (and hold the parameters)
-        const int col0 = sub * 128 + c4 * 32;
-        tmem_ld32(tlane + col0, v);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          float rs[8];
-          unpack8(*reinterpret_cast<const uint4*>(XS + a_off(r, col0 + i * 8)), rs);
-          const float4 b0 = *reinterpret_cast<const float4*>(bias + col0 + i * 8);        // shared memory (staged per layer)
-          const float4 b1 = *reinterpret_cast<const float4*>(bias + col0 + i * 8 + 4);
-          v[i * 8 + 0] += rs[0] + b0.x; v[i * 8 + 1] += rs[1] + b0.y; v[i * 8 + 2] += rs[2] + b0.z; v[i * 8 + 3] += rs[3] + b0.w;
-          v[i * 8 + 4] += rs[4] + b1.x; v[i * 8 + 5] += rs[5] + b1.y; v[i * 8 + 6] += rs[6] + b1.z; v[i * 8 + 7] += rs[7] + b1.w;
-        }
-#pragma unroll
-        for (int i = 0; i < 32; ++i) { sum += v[i]; sq = fmaf(v[i], v[i], sq); }
-        tmem_st32(tlane + col0, v);
+      for (int i = 0; i < 8; ++i) {
+        float rs[8];
+        unpack8(*reinterpret_cast<const uint4*>(XS + a_off(r, col0 + i * 8)), rs);
+        const float4 b0 = *reinterpret_cast<const float4*>(bias + col0 + i * 8);
+        const float4 b1 = *reinterpret_cast<const float4*>(bias + col0 + i * 8 + 4);
+        v[i * 8 + 0] += rs[0] + b0.x; v[i * 8 + 1] += rs[1] + b0.y; v[i * 8 + 2] += rs[2] + b0.z; v[i * 8 + 3] += rs[3] + b0.w;
+        v[i * 8 + 4] += rs[4] + b1.x; v[i * 8 + 5] += rs[5] + b1.y; v[i * 8 + 6] += rs[6] + b1.z; v[i * 8 + 7] += rs[7] + b1.w;
       }
-      red[(sub * 128 + r) * 2] = sum; red[(sub * 128 + r) * 2 + 1] = sq;
+#pragma unroll
+      for (int i = 0; i < 64; ++i) { sum += v[i]; sq = fmaf(v[i], v[i], sq); }
+      red_s[sub * 96 + r] = sum; red_q[sub * 96 + r] = sq;
       workers_sync();
-      sum = red[r * 2] + red[(128 + r) * 2]; sq = red[r * 2 + 1] + red[(128 + r) * 2 + 1];
+      sum = red_s[r] + red_s[96 + r] + red_s[192 + r] + red_s[288 + r];
+      sq = red_q[r] + red_q[96 + r] + red_q[192 + r] + red_q[288 + r];
       const float mean = sum * (1.0f / D);
       const float rstd = rsqrtf(fmaxf(sq * (1.0f / D) - mean * mean, 0.f) + 1e-5f);
-#pragma unroll 1
-      for (int c4 = 0; c4 < (q4 < 3 ? 4 : 0); ++c4) {
-        const int col0 = sub * 128 + c4 * 32;
-        tmem_ld32(tlane + col0, v);
 #pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-          const float4 g4 = *reinterpret_cast<const float4*>(gamma + col0 + i);          // shared memory (OFF_LNP)
-          const float4 b4 = *reinterpret_cast<const float4*>(beta + col0 + i);
-          v[i] = (v[i] - mean) * rstd * g4.x + b4.x; v[i + 1] = (v[i + 1] - mean) * rstd * g4.y + b4.y;
-          v[i + 2] = (v[i + 2] - mean) * rstd * g4.z + b4.z; v[i + 3] = (v[i + 3] - mean) * rstd * g4.w + b4.w;
-        }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(XS + a_off(r, col0 + i * 8)) = pack8(v + i * 8);
+      for (int i = 0; i < 64; i += 4) {
+        const float4 g4 = *reinterpret_cast<const float4*>(gamma + col0 + i);
+        const float4 b4 = *reinterpret_cast<const float4*>(beta + col0 + i);
+        v[i] = (v[i] - mean) * rstd * g4.x + b4.x; v[i + 1] = (v[i + 1] - mean) * rstd * g4.y + b4.y;
+        v[i + 2] = (v[i + 2] - mean) * rstd * g4.z + b4.z; v[i + 3] = (v[i + 3] - mean) * rstd * g4.w + b4.w;
       }
-      workers_sync();                               // `red` is reused by the next LayerNorm
-      release_acc(0, 1, true, -1);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) *reinterpret_cast<uint4*>(XS + a_off(r, col0 + i * 8)) = pack8(v + i * 8);
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars[B_XSR]);
+      // `red` is rewritten by the next LayerNorm only after several more worker barriers
       lap(PF_W_LN);
     };
     auto debug_dump = [&](int slot, int clip) {
       if (!P.debug) return;
       workers_sync();
       if (r < S) {
-        float* o = P.dbg + (long long)slot * P.dbg_slot + ((long long)clip * S + r) * D + sub * 128;
-        for (int c8 = 0; c8 < 16; ++c8) {
+        float* o = P.dbg + (long long)slot * P.dbg_slot + ((long long)clip * S + r) * D + sub * 64;
+        for (int c8 = 0; c8 < 8; ++c8) {
           float t8[8];
-          unpack8(*reinterpret_cast<const uint4*>(XS + a_off(r, sub * 128 + c8 * 8)), t8);
+          unpack8(*reinterpret_cast<const uint4*>(XS + a_off(r, sub * 64 + c8 * 8)), t8);
           for (int i = 0; i < 8; ++i) o[c8 * 8 + i] = t8[i];
         }
       }
     };
 
-    for (int i = wt; i < JPAD; i += 256)               // pose-head bias -> token-less rows of XS k-tiles 1 and 2
+    for (int i = wt; i < JPAD; i += NWT)               // pose-head bias -> token-less rows of XS k-tiles 1 and 2
       *reinterpret_cast<float*>(smem + (i < 1024 ? OFF_BOUT0 + i * 4 : OFF_BOUT1 + (i - 1024) * 4)) = __ldg(P.bout + i);
     for (int clip = blockIdx.x; clip < P.B; clip += gridDim.x) {
       float* xc = P.x + (long long)clip * J * T;
@@ -491,14 +511,15 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
         tcgen05_fence_after();
         // BUF held x_t / z chunks and A k-blocks since the last step: the pad rows of the Z staging (read as V with zero weight
         // by the last windows) must be finite
-        for (int i = wt; i < (ZROWS - T) * 33; i += 256)
+        for (int i = wt; i < (ZROWS - T) * 33; i += NWT)
           reinterpret_cast<uint4*>(Zs + (T + i / 33) * ZLD)[i % 33] = make_uint4(0u, 0u, 0u, 0u);
         {
           const int f = r - 1;
           const bool ok = r >= 1 && r <= T;
+          float v[32];
 #pragma unroll 1
-          for (int c4 = 0; c4 < 4; ++c4) {
-            const int col0 = sub * 128 + c4 * 32;      // == local head (sub*4 + c4) * 32
+          for (int c2 = 0; c2 < 2; ++c2) {
+            const int col0 = sub * 64 + c2 * 32;       // == local head (sub*2 + c2) * 32
             tmem_ld32(tlane + col0, v);
             if (!ok) continue;
             const float* cr = condc + (long long)f * D + col0;
@@ -524,7 +545,7 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
         workers_sync();
         lap(PF_W_IN_EPI);
         // ---------------- windowed causal local attention on mma.sync (q = k = v = Z), rotary (position = frame + 1) -> XS
-        for (int item = ww; item < 64; item += 8) {
+        for (int item = wl; item < 64; item += NW) {
           const int w = item >> 3, lh = item & 7;
           const int q0 = WIN * w, k0 = (w == 0) ? 0 : WIN * (w - 1), nk = q0 + WIN - k0;
           float sc[4][4];
@@ -601,7 +622,7 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
             }
           }
         }
-        {   // token row: tok = emb_1 + emb_t (rotary at position 0 is the identity)
+        if (wt < D) {   // token row: tok = emb_1 + emb_t (rotary at position 0 is the identity)
           const float tv = __ldg(P.emb1 + (long long)clip * D + wt) + __ldg(P.te + (long long)trow * D + wt);
           *reinterpret_cast<__nv_bfloat16*>(XS + a_off(0, wt)) = __float2bfloat16_rn(tv);
         }
@@ -614,24 +635,22 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
         // ---------------- transformer layers
         for (int l = 0; l < NL; ++l) {
           const float* lp = P.lparams + (long long)l * P_SIZE;
-          // With 225 KB of shared memory the L1 is a few KB: every parameter read is an L2 round trip.  The hottest one
-          // (linear1's bias, read by 64 GELU epilogues per step) is staged in shared memory once per layer; the first
-          // named barrier of the attention phase orders it before its first use.
-          {
-            const float4 t4 = __ldg(reinterpret_cast<const float4*>(lp + P_B1) + wt);
-            reinterpret_cast<__half2*>(b1s)[2 * wt] = __floats2half2_rn(t4.x, t4.y);
-            reinterpret_cast<__half2*>(b1s)[2 * wt + 1] = __floats2half2_rn(t4.z, t4.w);
-            // LayerNorm gains / biases -> the spare rows of XS (g1 | be1 are contiguous in lparams, so are g2 | be2)
-            const int which = wt >> 7, i4 = wt & 127;
-            lnp4[wt] = __ldg(reinterpret_cast<const float4*>(lp + (which ? P_G2 : P_G1)) + i4);
-          }
-          if (wt < 64) {                                 // q bias (per head, [h][64]); the k bias drops out of the softmax,
-            const int h = wt >> 4, i4 = wt & 15;        // the v bias is folded into bo' = bo + Wo bv at set-up
-            reinterpret_cast<float4*>(b1s + 1024)[wt] = __ldg(reinterpret_cast<const float4*>(lp + P_BQKV + h * 192) + i4);
-          } else if (wt < 128) {
-            reinterpret_cast<float4*>(b1s + 1280)[wt - 64] = __ldg(reinterpret_cast<const float4*>(lp + P_BO) + (wt - 64));
-          } else if (wt < 192) {
-            reinterpret_cast<float4*>(b1s + 1536)[wt - 128] = __ldg(reinterpret_cast<const float4*>(lp + P_B2) + (wt - 128));
+          // With 225 KB of shared memory the L1 is a few KB: every parameter read would be an L2 round trip, so the layer's
+          // parameters are staged in shared memory once; the first barrier of the attention phase orders them before use.
+          for (int i = wt; i < 448; i += NWT) {
+            if (i < 256) {                               // linear1 bias as fp16; LayerNorm gains / biases (g1|be1 and g2|be2 are contiguous)
+              const float4 t4 = __ldg(reinterpret_cast<const float4*>(lp + P_B1) + i);
+              reinterpret_cast<__half2*>(b1s)[2 * i] = __floats2half2_rn(t4.x, t4.y);
+              reinterpret_cast<__half2*>(b1s)[2 * i + 1] = __floats2half2_rn(t4.z, t4.w);
+              reinterpret_cast<float4*>(lnp)[i] = __ldg(reinterpret_cast<const float4*>(lp + ((i >> 7) ? P_G2 : P_G1)) + (i & 127));
+            } else if (i < 320) {                        // q bias (per head, [h][64]); the k bias drops out of the softmax,
+              const int j = i - 256, h = j >> 4, i4 = j & 15;   // the v bias is folded into bo' = bo + Wo bv at set-up
+              reinterpret_cast<float4*>(b1s + 1024)[j] = __ldg(reinterpret_cast<const float4*>(lp + P_BQKV + h * 192) + i4);
+            } else if (i < 384) {
+              reinterpret_cast<float4*>(b1s + 1280)[i - 320] = __ldg(reinterpret_cast<const float4*>(lp + P_BO) + (i - 320));
+            } else {
+              reinterpret_cast<float4*>(b1s + 1536)[i - 384] = __ldg(reinterpret_cast<const float4*>(lp + P_B2) + (i - 384));
+            }
           }
           workers_sync();
           for (int h = 0; h < NH; ++h) {
@@ -639,46 +658,49 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
             ph.wait(bars, B_ACCR + 2 * hb); ph.wait(bars, B_ACCR + 2 * hb + 1);
             lap(PF_W_QKV_WAIT);
             tcgen05_fence_after();
-            // q | k | v of this head: 6 chunks of 32 columns; column-half 0 takes q0 q1 k0, half 1 takes k1 v0 v1
+            // q | k | v of this head: 12 chunks of 16 columns, three per column quarter
 #pragma unroll 1
             for (int ci = 0; ci < 3; ++ci) {
-              const int ch = sub * 3 + ci;               // 0..5
-              tmem_ld32(tlane + hb * 256 + ch * 32, v);
-              if (r >= 96) continue;
-              __nv_bfloat16* dst = (ch < 2 ? Qs : (ch < 4 ? Ks : Vs)) + r * QLD + (ch & 1) * 32;
+              const int ch = sub * 3 + ci;               // 0..11: q = 0..3, k = 4..7, v = 8..11
+              float v16[16];
+              tmem_ld16_issue(tlane + hb * 256 + ch * 16, v16);
+              tmem_ld_wait();
+              __nv_bfloat16* dst = (ch < 4 ? Qs : (ch < 8 ? Ks : Vs)) + r * QLD + (ch & 3) * 16;
               if (r < S) {
-                if (ch < 2) {
-                  const float* bq = b1s + 1024 + h * 64 + ch * 32;
+                if (ch < 4) {
+                  const float* bq = b1s + 1024 + h * 64 + ch * 16;
 #pragma unroll
-                  for (int i = 0; i < 32; i += 4) {
+                  for (int i = 0; i < 16; i += 4) {
                     const float4 b4 = *reinterpret_cast<const float4*>(bq + i);
-                    v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
+                    v16[i] += b4.x; v16[i + 1] += b4.y; v16[i + 2] += b4.z; v16[i + 3] += b4.w;
                   }
                 }
-#pragma unroll
-                for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(dst + i * 8) = pack8(v + i * 8);
+                *reinterpret_cast<uint4*>(dst) = pack8(v16);
+                *reinterpret_cast<uint4*>(dst + 8) = pack8(v16 + 8);
               } else {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(dst + i * 8) = make_uint4(0u, 0u, 0u, 0u);
+                *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u);
+                *reinterpret_cast<uint4*>(dst + 8) = make_uint4(0u, 0u, 0u, 0u);
               }
             }
             release_acc(2 * hb, 2 * hb + 1, false, -1);
             if (l > 0 && hb == 0) ph.wait(bars, B_BUFF + (h >> 1));    // linear2 of the previous layer has consumed this BUF half
             workers_sync();
-            if (ww * 16 < S) {
-              // ---- softmax(q k^T / 8) v for query rows 16*ww .. +15 (FlashAttention-2 register reuse)
-              const int r0 = ww * 16;
-              float sc[12][4];
+            {
+              // ---- softmax(q k^T / 8) v: warp = (16 query rows, one half of the keys); the two partial results of a row block
+              // are merged flash-style through 36 spare TMEM columns of the pair's lane quarter
+              const int rb = q4 * 2 + (sub & 1), kh = sub >> 1;
+              const int r0 = rb * 16, key0 = kh * 48;
+              float sc[6][4];
 #pragma unroll
-              for (int nt = 0; nt < 12; ++nt) { sc[nt][0] = sc[nt][1] = sc[nt][2] = sc[nt][3] = 0.f; }
+              for (int nt = 0; nt < 6; ++nt) { sc[nt][0] = sc[nt][1] = sc[nt][2] = sc[nt][3] = 0.f; }
 #pragma unroll
               for (int kk = 0; kk < 4; ++kk) {
                 uint32_t a[4];
                 ldsm_x4(a[0], a[1], a[2], a[3], Qs + (r0 + (lane & 7) + ((lane >> 3) & 1) * 8) * QLD + kk * 16 + (lane >> 4) * 8);
 #pragma unroll
-                for (int np = 0; np < 6; ++np) {
+                for (int np = 0; np < 3; ++np) {
                   uint32_t b0, b1, b2, b3;
-                  ldsm_x4(b0, b1, b2, b3, Ks + (np * 16 + (lane & 7) + (lane >> 4) * 8) * QLD + kk * 16 + ((lane >> 3) & 1) * 8);
+                  ldsm_x4(b0, b1, b2, b3, Ks + (key0 + np * 16 + (lane & 7) + (lane >> 4) * 8) * QLD + kk * 16 + ((lane >> 3) & 1) * 8);
                   mma_bf16_16816(sc[2 * np], a, b0, b1);
                   mma_bf16_16816(sc[2 * np + 1], a, b2, b3);
                 }
@@ -686,8 +708,8 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
               const int cbase = (lane & 3) * 2;
               float mx0 = -3.0e38f, mx1 = -3.0e38f;
 #pragma unroll
-              for (int nt = 0; nt < 12; ++nt) {
-                const int c = nt * 8 + cbase;
+              for (int nt = 0; nt < 6; ++nt) {
+                const int c = key0 + nt * 8 + cbase;
                 if (c >= S) { sc[nt][0] = -3.0e38f; sc[nt][2] = -3.0e38f; }
                 if (c + 1 >= S) { sc[nt][1] = -3.0e38f; sc[nt][3] = -3.0e38f; }
                 mx0 = fmaxf(mx0, fmaxf(sc[nt][0], sc[nt][1]));
@@ -698,36 +720,57 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
               const float sl2 = 1.4426950408889634f * 0.125f;
               float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-              for (int nt = 0; nt < 12; ++nt) {
+              for (int nt = 0; nt < 6; ++nt) {
                 sc[nt][0] = exp2f((sc[nt][0] - mx0) * sl2); sc[nt][1] = exp2f((sc[nt][1] - mx0) * sl2);
                 sc[nt][2] = exp2f((sc[nt][2] - mx1) * sl2); sc[nt][3] = exp2f((sc[nt][3] - mx1) * sl2);
                 s0 += sc[nt][0] + sc[nt][1]; s1 += sc[nt][2] + sc[nt][3];
               }
               s0 += __shfl_xor_sync(0xffffffffu, s0, 1); s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
               s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
-              float oc[8][4];
+              float oc[36];                              // [8 d-tiles][4] + (mx0, mx1, s0, s1)
 #pragma unroll
-              for (int dt = 0; dt < 8; ++dt) { oc[dt][0] = oc[dt][1] = oc[dt][2] = oc[dt][3] = 0.f; }
+              for (int i = 0; i < 32; ++i) oc[i] = 0.f;
 #pragma unroll
-              for (int kt = 0; kt < 6; ++kt) {
+              for (int kt = 0; kt < 3; ++kt) {
                 uint32_t a[4];
                 a[0] = pack_bf16x2(sc[2 * kt][0], sc[2 * kt][1]); a[1] = pack_bf16x2(sc[2 * kt][2], sc[2 * kt][3]);
                 a[2] = pack_bf16x2(sc[2 * kt + 1][0], sc[2 * kt + 1][1]); a[3] = pack_bf16x2(sc[2 * kt + 1][2], sc[2 * kt + 1][3]);
 #pragma unroll
                 for (int dp = 0; dp < 4; ++dp) {
                   uint32_t b0, b1, b2, b3;
-                  ldsm_x4_t(b0, b1, b2, b3, Vs + (kt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * QLD + dp * 16 + (lane >> 4) * 8);
-                  mma_bf16_16816(oc[2 * dp], a, b0, b1);
-                  mma_bf16_16816(oc[2 * dp + 1], a, b2, b3);
+                  ldsm_x4_t(b0, b1, b2, b3, Vs + (key0 + kt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * QLD + dp * 16 + (lane >> 4) * 8);
+                  mma_bf16_16816(*reinterpret_cast<float(*)[4]>(oc + 8 * dp), a, b0, b1);
+                  mma_bf16_16816(*reinterpret_cast<float(*)[4]>(oc + 8 * dp + 4), a, b2, b3);
                 }
               }
-              const float i0 = 1.0f / s0, i1 = 1.0f / s1;
-              const int row0 = r0 + (lane >> 2), row1 = row0 + 8;
+              const uint32_t scratch = tlane + (uint32_t)((sub & 1) * 256 + 192);
+              if (kh == 1) {
+                oc[32] = mx0; oc[33] = mx1; oc[34] = s0; oc[35] = s1;
+                tmem_st32(scratch, oc);
+                tmem_st4(scratch + 32, oc + 32);
+                tcgen05_fence_before();
+              }
+              pair_sync(2 + rb);
+              if (kh == 0) {
+                float ob[36];
+                tcgen05_fence_after();
+                tmem_ld32_issue(scratch, ob); tmem_ld4_issue(scratch + 32, ob + 32);
+                tmem_ld_wait(); tie32(ob); tie4(ob + 32);
+                // (m, s, O) of the two key halves -> one softmax: scale each side by 2^((m_side - m) / 8 * log2 e)
+                const float m0 = fmaxf(mx0, ob[32]), m1 = fmaxf(mx1, ob[33]);
+                const float fa0 = exp2f((mx0 - m0) * sl2), fb0 = exp2f((ob[32] - m0) * sl2);
+                const float fa1 = exp2f((mx1 - m1) * sl2), fb1 = exp2f((ob[33] - m1) * sl2);
+                const float i0 = 1.0f / (s0 * fa0 + ob[34] * fb0), i1 = 1.0f / (s1 * fa1 + ob[35] * fb1);
+                const float a0 = fa0 * i0, b0 = fb0 * i0, a1 = fa1 * i1, b1 = fb1 * i1;
+                const int row0 = r0 + (lane >> 2), row1 = row0 + 8;
 #pragma unroll
-              for (int dt = 0; dt < 8; ++dt) {
-                const int c = h * HD + dt * 8 + cbase;
-                *reinterpret_cast<uint32_t*>(BUF + a_off(row0, c)) = pack_bf16x2(oc[dt][0] * i0, oc[dt][1] * i0);
-                *reinterpret_cast<uint32_t*>(BUF + a_off(row1, c)) = pack_bf16x2(oc[dt][2] * i1, oc[dt][3] * i1);
+                for (int dt = 0; dt < 8; ++dt) {
+                  const int c = h * HD + dt * 8 + cbase;
+                  *reinterpret_cast<uint32_t*>(BUF + a_off(row0, c)) =
+                      pack_bf16x2(oc[4 * dt] * a0 + ob[4 * dt] * b0, oc[4 * dt + 1] * a0 + ob[4 * dt + 1] * b0);
+                  *reinterpret_cast<uint32_t*>(BUF + a_off(row1, c)) =
+                      pack_bf16x2(oc[4 * dt + 2] * a1 + ob[4 * dt + 2] * b1, oc[4 * dt + 3] * a1 + ob[4 * dt + 3] * b1);
+                }
               }
             }
             fence_async_smem();
@@ -736,7 +779,7 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
             lap(PF_W_ATT);
           }
           layernorm_epilogue(b1s + 1280, lnp, lnp + 256);
-          // ---- FFN: GELU epilogue per 128-unit chunk -> BUF half (c & 1) as the A operand of linear2
+          // ---- FFN: GELU epilogue per 128-unit chunk -> BUF half (c & 1) as the (fp16) A operand of linear2
           for (int c = 0; c < 8; ++c) {
             const int qd = 2 + (c & 1);
             ph.wait(bars, B_ACCR + qd);
@@ -744,29 +787,22 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
             lap(PF_W_GELU_WAIT);
             tcgen05_fence_after();
             {
-              float va[32], vb[32];
-              const int cc0 = sub * 64;                  // column inside the chunk
-              tmem_ld32_issue(tlane + qd * 128 + cc0, va); tmem_ld32_issue(tlane + qd * 128 + cc0 + 32, vb);
-              tmem_ld_wait(); tie32(va); tie32(vb);
+              float va[32];
+              const int cc0 = sub * 32;                  // column inside the chunk
+              tmem_ld32_issue(tlane + qd * 128 + cc0, va);
+              tmem_ld_wait(); tie32(va);
               tcgen05_fence_before();
               __syncwarp();
               if (lane == 0) mbar_arrive(&bars[B_ACCF + qd]);      // accumulator free: values are in registers now
               // GELU in packed fp16 (tanh form on MUFU.TANH, 4 instructions per element): the hidden is stored as fp16, which
               // keeps 3 more mantissa bits than the bf16 it replaces; |half-tanh GELU - exact| rms 5e-4 vs 2e-3 for bf16(exact)
-              if (q4 < 3) {
-                const __half2* b1h = reinterpret_cast<const __half2*>(b1s) + ((c * 128 + cc0) >> 1);
-                uint32_t ha[16], hb[16];
+              const __half2* b1h = reinterpret_cast<const __half2*>(b1s) + ((c * 128 + cc0) >> 1);
+              uint32_t ha[16];
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                  ha[i] = gelu_h2(__hadd2(__floats2half2_rn(va[2 * i], va[2 * i + 1]), b1h[i]));
-                  hb[i] = gelu_h2(__hadd2(__floats2half2_rn(vb[2 * i], vb[2 * i + 1]), b1h[16 + i]));
-                }
+              for (int i = 0; i < 16; ++i) ha[i] = gelu_h2(__hadd2(__floats2half2_rn(va[2 * i], va[2 * i + 1]), b1h[i]));
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  *reinterpret_cast<uint4*>(BUF + a_off(r, (c & 1) * 128 + cc0 + i * 8)) = make_uint4(ha[4 * i], ha[4 * i + 1], ha[4 * i + 2], ha[4 * i + 3]);
-                  *reinterpret_cast<uint4*>(BUF + a_off(r, (c & 1) * 128 + cc0 + 32 + i * 8)) = make_uint4(hb[4 * i], hb[4 * i + 1], hb[4 * i + 2], hb[4 * i + 3]);
-                }
-              }
+              for (int i = 0; i < 4; ++i)
+                *reinterpret_cast<uint4*>(BUF + a_off(r, (c & 1) * 128 + cc0 + i * 8)) = make_uint4(ha[4 * i], ha[4 * i + 1], ha[4 * i + 2], ha[4 * i + 3]);
             }
             fence_async_smem();
             __syncwarp();
@@ -778,7 +814,7 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
         }
 
         // ---------------- pose head + posterior: x <- f(x0, x, z) in place (fp32, global) and as next step's bf16 A k-blocks.
-        // Chunk c = 32 joint channels (TMEM quarter (c >> 2) & 3, columns (c & 3) * 32); the two column halves take 16 each.
+        // Chunk c = 32 joint channels (TMEM quarter (c >> 2) & 3, columns (c & 3) * 32); the four column quarters take 8 each.
         lap(PF_W_ZWAIT);
         {
           const float4 cf = P.coef[index];
@@ -790,27 +826,25 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
             ph.wait(bars, B_HFULL + sl);
             lap(PF_W_HEAD_WAIT);
             tcgen05_fence_after();
-            const int j0 = c * HCH + sub * 16;
-            float v16[16];
-            tmem_ld16_issue(tlane + (t & 3) * 128 + sl * 32 + sub * 16, v16);
+            const int j0 = c * HCH + sub * 8;
+            float v8[8];
+            tmem_ld8_issue(tlane + (t & 3) * 128 + sl * 32 + sub * 8, v8);
             tmem_ld_wait();
             if (ok && j0 < J) {
-              const float* xs = reinterpret_cast<const float*>(smem + hslot_x(sl)) + sub * 16 * T + f;
-              const float* zs = reinterpret_cast<const float*>(smem + hslot_z(sl)) + sub * 16 * T + f;
+              const float* xs = reinterpret_cast<const float*>(smem + hslot_x(sl)) + sub * 8 * T + f;
+              const float* zs = reinterpret_cast<const float*>(smem + hslot_z(sl)) + sub * 8 * T + f;
               const float* bo = reinterpret_cast<const float*>(smem + (j0 < 1024 ? OFF_BOUT0 + j0 * 4 : OFF_BOUT1 + (j0 - 1024) * 4));
               float* xg = xc + (long long)j0 * T + f;
 #pragma unroll
-              for (int i = 0; i < 16; ++i) {
+              for (int i = 0; i < 8; ++i) {
                 const bool in = j0 + i < J;
                 const float xt = in ? xs[i * T] : 0.f, zz = (nz && in) ? zs[i * T] : 0.f;
-                const float x0 = v16[i] + bo[i];
-                v16[i] = in ? posterior_apply(P.sampler, cf, x0, xt, zz, nz) : 0.f;
-                if (in) xg[(long long)i * T] = v16[i];
+                const float x0 = v8[i] + bo[i];
+                v8[i] = in ? posterior_apply(P.sampler, cf, x0, xt, zz, nz) : 0.f;
+                if (in) xg[(long long)i * T] = v8[i];
               }
               uint8_t* row = xac + (long long)(j0 >> 6) * KT + (r >> 3) * 1024 + (r & 7) * 128;
-              const int c8 = (j0 & 63) >> 3;
-              *reinterpret_cast<uint4*>(row + (((c8) ^ (r & 7)) << 4)) = pack8(v16);
-              *reinterpret_cast<uint4*>(row + (((c8 + 1) ^ (r & 7)) << 4)) = pack8(v16 + 8);
+              *reinterpret_cast<uint4*>(row + ((((j0 & 63) >> 3) ^ (r & 7)) << 4)) = pack8(v8);
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&bars[B_HEMPTY + sl]);
@@ -827,7 +861,7 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
   }
   tcgen05_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == 7) {
     tcgen05_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
   }

@@ -116,8 +116,8 @@ static int clip_run(dsg_engine* e, int B, float* xd, int n_run, int first_index,
   const int grid = B < e->num_sms ? B : e->num_sms;
   clip::pack_xa_kernel<<<dim3(clip::JPAD / 64, B), 256, 0, st>>>(xd, t->xa);       // x_T as the first step's A k-blocks
   e->launches++;
-  if (p.prof) clip::clip_kernel<true><<<grid, 384, clip::SMEM_BYTES, st>>>(t->tm_cin, t->tm_c128, t->tm_c64, t->tm_cw2, p);
-  else clip::clip_kernel<false><<<grid, 384, clip::SMEM_BYTES, st>>>(t->tm_cin, t->tm_c128, t->tm_c64, t->tm_cw2, p);
+  if (p.prof) clip::clip_kernel<true><<<grid, 512, clip::SMEM_BYTES, st>>>(t->tm_cin, t->tm_c128, t->tm_c64, t->tm_cw2, p);
+  else clip::clip_kernel<false><<<grid, 512, clip::SMEM_BYTES, st>>>(t->tm_cin, t->tm_c128, t->tm_c64, t->tm_cw2, p);
   e->launches++;
   CUDA_TRY(cudaGetLastError());
   return DSG_OK;
