@@ -133,7 +133,8 @@ DSG_DEVINL void unpack8(const uint4 u, float* v) {
 
 // cycle counters (CTA 0): where each role spends its time
 enum { PF_TOTAL = 0, PF_MMA_WAIT_W, PF_MMA_WAIT_OTHER, PF_PROD_WAIT_EMPTY, PF_W_STAGE, PF_W_IN_WAIT, PF_W_IN_EPI, PF_W_LOCAL,
-       PF_W_QKV_WAIT, PF_W_ATT, PF_W_LN_WAIT, PF_W_LN, PF_W_GELU_WAIT, PF_W_GELU, PF_W_HEAD_WAIT, PF_W_HEAD, PF_W_ZWAIT, PF_COUNT };
+       PF_W_QKV_WAIT, PF_W_ATT, PF_W_LN_WAIT, PF_W_LN, PF_W_GELU_WAIT, PF_W_GELU, PF_W_HEAD_WAIT, PF_W_HEAD, PF_W_ZWAIT,
+       PF_W_EXTRACT, PF_W_SYNC1, PF_W_ATT_MMA, PF_W_ATT_MERGE, PF_COUNT };
 
 // consumers of tcgen05.ld results must not be scheduled above tcgen05.wait::ld: pass the registers through an empty
 // volatile asm placed after the wait
@@ -658,33 +659,40 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
             ph.wait(bars, B_ACCR + 2 * hb); ph.wait(bars, B_ACCR + 2 * hb + 1);
             lap(PF_W_QKV_WAIT);
             tcgen05_fence_after();
-            // q | k | v of this head: 12 chunks of 16 columns, three per column quarter
-#pragma unroll 1
-            for (int ci = 0; ci < 3; ++ci) {
-              const int ch = sub * 3 + ci;               // 0..11: q = 0..3, k = 4..7, v = 8..11
-              float v16[16];
-              tmem_ld16_issue(tlane + hb * 256 + ch * 16, v16);
-              tmem_ld_wait();
-              __nv_bfloat16* dst = (ch < 4 ? Qs : (ch < 8 ? Ks : Vs)) + r * QLD + (ch & 3) * 16;
-              if (r < S) {
-                if (ch < 4) {
-                  const float* bq = b1s + 1024 + h * 64 + ch * 16;
+            // q | k | v of this head: 12 chunks of 16 columns, three per column quarter (one wait for the three TMEM loads)
+            {
+              float v48[48];
+              tmem_ld16_issue(tlane + hb * 256 + (sub * 3) * 16, v48);
+              tmem_ld16_issue(tlane + hb * 256 + (sub * 3 + 1) * 16, v48 + 16);
+              tmem_ld16_issue(tlane + hb * 256 + (sub * 3 + 2) * 16, v48 + 32);
+              tmem_ld_wait(); tie32(v48); tie4(v48 + 32); tie4(v48 + 36); tie4(v48 + 40); tie4(v48 + 44);
 #pragma unroll
-                  for (int i = 0; i < 16; i += 4) {
-                    const float4 b4 = *reinterpret_cast<const float4*>(bq + i);
-                    v16[i] += b4.x; v16[i + 1] += b4.y; v16[i + 2] += b4.z; v16[i + 3] += b4.w;
+              for (int ci = 0; ci < 3; ++ci) {
+                const int ch = sub * 3 + ci;             // 0..11: q = 0..3, k = 4..7, v = 8..11
+                float* v16 = v48 + 16 * ci;
+                __nv_bfloat16* dst = (ch < 4 ? Qs : (ch < 8 ? Ks : Vs)) + r * QLD + (ch & 3) * 16;
+                if (r < S) {
+                  if (ch < 4) {
+                    const float* bq = b1s + 1024 + h * 64 + ch * 16;
+#pragma unroll
+                    for (int i = 0; i < 16; i += 4) {
+                      const float4 b4 = *reinterpret_cast<const float4*>(bq + i);
+                      v16[i] += b4.x; v16[i + 1] += b4.y; v16[i + 2] += b4.z; v16[i + 3] += b4.w;
+                    }
                   }
+                  *reinterpret_cast<uint4*>(dst) = pack8(v16);
+                  *reinterpret_cast<uint4*>(dst + 8) = pack8(v16 + 8);
+                } else {
+                  *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u);
+                  *reinterpret_cast<uint4*>(dst + 8) = make_uint4(0u, 0u, 0u, 0u);
                 }
-                *reinterpret_cast<uint4*>(dst) = pack8(v16);
-                *reinterpret_cast<uint4*>(dst + 8) = pack8(v16 + 8);
-              } else {
-                *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u);
-                *reinterpret_cast<uint4*>(dst + 8) = make_uint4(0u, 0u, 0u, 0u);
               }
             }
             release_acc(2 * hb, 2 * hb + 1, false, -1);
             if (l > 0 && hb == 0) ph.wait(bars, B_BUFF + (h >> 1));    // linear2 of the previous layer has consumed this BUF half
+            lap(PF_W_EXTRACT);
             workers_sync();
+            lap(PF_W_SYNC1);
             {
               // ---- softmax(q k^T / 8) v: warp = (16 query rows, one half of the keys); the two partial results of a row block
               // are merged flash-style through 36 spare TMEM columns of the pair's lane quarter
@@ -743,6 +751,7 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
                   mma_bf16_16816(*reinterpret_cast<float(*)[4]>(oc + 8 * dp + 4), a, b2, b3);
                 }
               }
+              lap(PF_W_ATT_MMA);
               const uint32_t scratch = tlane + (uint32_t)((sub & 1) * 256 + 192);
               if (kh == 1) {
                 oc[32] = mx0; oc[33] = mx1; oc[34] = s0; oc[35] = s1;
@@ -773,6 +782,7 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
                 }
               }
             }
+            lap(PF_W_ATT_MERGE);
             fence_async_smem();
             workers_sync();                              // staging may be overwritten; this head's k-tile of BUF is complete
             if (hb == 1 && lane == 0) mbar_arrive(&bars[B_BUFR + (h >> 1)]);
