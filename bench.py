@@ -356,11 +356,12 @@ def main():
                         "launches_per_segment": nl, "us_per_ddpm_step": ms * 1e3 / diffusion.num_timesteps,
                         "note": "segment call timed with CUDA events (conditioning GEMMs + x_T draw + the loop kernel); "
                                 "FLOPs = reference's 2*M*N*K count, excludes padding (89 -> 128 token rows) and hoisted terms"}
-            # HBM traffic of the launch: x_t is read twice and written once, the pre-drawn noise is written and read once
-            # per clip-step (everything else is on chip or L2-resident weights): ncu measured 1.72 MB per clip-step
-            # (profiles/r01_clip_kernel_ncu_full_summary.csv: dram read + write of a 148-clip x 12-step launch)
-            roofline["traffic"] = 1.72e6 * B * diffusion.num_timesteps
-            roofline["traffic_note"] = "bytes per launch = ncu dram__bytes_read+write per clip-step (1.72 MB, r01 capture) x clips x steps"
+            # HBM traffic of the launch: x_t read and written once (fp32), its bf16 k-block image written and read once, the
+            # pre-drawn noise written and read once per clip-step (everything else is on chip or L2-resident weights): ncu
+            # measured 1.99 MB per clip-step (profiles/r01_clip_kernel_v4_ncu_full_summary.csv: dram read + write of a
+            # 148-clip x 12-step launch = 3.529 GB)
+            roofline["traffic"] = 1.987e6 * B * diffusion.num_timesteps
+            roofline["traffic_note"] = "bytes per launch = ncu dram__bytes_read+write per clip-step (1.99 MB, r01 v4 capture) x clips x steps"
             log("clip-kernel segment: %.1f ms (%.1f us per DDPM step), %.1f TFLOP/s" % (ms, ms * 1e3 / diffusion.num_timesteps, ach))
             try:      # where the persistent kernel spends its cycles (instrumented build of the same kernel, 50 steps)
                 os.environ["DSG_CLIP_PROF"] = "1"
