@@ -138,7 +138,9 @@ def cpu_baseline(sample_steps, batch, threads):
 WAVLM_FLOP_PER_SEGMENT = 162.5e9      # 70,400 samples -> 219 frames: convs 21.6 + pos-conv 3.7 + 24 layers 137 GFLOP
 
 
-def bench_wavlm(dev, batch, peaks, frames_per_s_per_gpu):
+def bench_wavlm(dev, batch, peaks, frames_per_s_per_gpu, pipeline=None):
+    """Side measurements (rank 0): the WavLM-Large forward alone, and — `pipeline` = (run_from_features, B, nseg, n_frames) —
+    the whole path from raw 16 kHz waveforms in pinned host memory to motions in host memory (WavLM + diffusion)."""
     from diffusestylegesture_b200.wavlm import WavLM
     from diffusestylegesture_b200.wavlm_config import WAVLM_LARGE, synthetic_wavlm_state_dict, synthetic_wav
     log("wavlm: building synthetic WavLM-Large (315 M parameters)")
@@ -167,6 +169,27 @@ def bench_wavlm(dev, batch, peaks, frames_per_s_per_gpu):
            "share_of_clip_time": (frames_per_s_per_gpu / (seg_per_s * 80)) if frames_per_s_per_gpu else None,
            "note": "one 70,400-sample window per 80 new frames; share_of_clip_time = WavLM time / diffusion time for the same frames"}
     log("wavlm: %.2f ms per %d segments, %.0f TFLOP/s" % (ms, batch, ach))
+    if pipeline is not None:
+        run_from_features, B, nseg, n_frames = pipeline
+        # every clip gets its own waveform windows: [nseg][B, 70400] (8 seed frames of the previous window + 80 new frames)
+        wavs = [torch.cat([wav] * ((B + batch - 1) // batch))[:B].contiguous().pin_memory() for _ in range(nseg)]
+
+        def once():
+            feats = [m.wav2wavlm(w, 88) for w in wavs]          # host -> device inside dsg_wavlm_forward
+            return run_from_features(feats)                       # motions come back in host memory
+
+        once()
+        torch.cuda.synchronize(dev)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        out = once()
+        b.record()
+        torch.cuda.synchronize(dev)
+        ms2 = a.elapsed_time(b)
+        res["from_waveform"] = {"value": B * n_frames / (ms2 * 1e-3), "unit": UNIT, "ms_per_step": ms2, "clips": B,
+                                "h2d_bytes_per_step": int(sum(w.numel() * 4 for w in wavs)), "d2h_bytes_per_step": int(out.numel() * 4),
+                                "note": "one step = raw waveform windows in pinned host memory -> WavLM-Large -> 4 x 1000-step DDPM -> motions in host memory"}
+        log("waveform -> motion: %.1f ms per step, %.0f frames/s" % (ms2, res["from_waveform"]["value"]))
     m.close()
     return res
 
@@ -413,7 +436,8 @@ def main():
     wavlm = None
     if rank == 0 and not args.no_wavlm and precision == "bf16":
         try:
-            wavlm = bench_wavlm(dev, args.wavlm_batch, peaks, value / world)
+            pipe = None if args.no_e2e else ((lambda feats: one_step(feats, "cpu")), B, nseg, n_frames)
+            wavlm = bench_wavlm(dev, args.wavlm_batch, peaks, value / world, pipe)
         except (RuntimeError, NotImplementedError) as ex:
             sys.stderr.write(f"wavlm measurement unavailable: {ex}\n")
 

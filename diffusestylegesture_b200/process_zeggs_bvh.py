@@ -105,10 +105,9 @@ def pose2bvh_arrays(poses, length, smoothing=False):
     """Numeric part of pose2bvh + write_bvh: returns (positions [3*length, 75, 3], euler degrees [3*length, 75, 3])."""
     poses = np.asarray(poses)
     if smoothing:
-        sm = np.zeros((poses.shape[0], poses.shape[1]))
-        for c in range(poses.shape[1]):
-            sm[:, c] = savgol_filter(poses[:, c], 15, 2)     # NOTE(reference): smoothing rotation matrices is not optimal
-        poses = sm
+        # the reference filters column by column (process_zeggs_bvh.py:224-227); one call along axis 0 is the same filter
+        # (differences ~3e-15, far below the %f of the writer) and 5x faster.  NOTE(reference): smoothing rotation matrices is not optimal
+        poses = savgol_filter(np.asarray(poses, dtype=np.float64), 15, 2, axis=0)
     nj = NJOINTS
     root_pos, root_rot = poses[:, 0:3], poses[:, 3:7]
     lpos = poses[:, 13: 13 + nj * 3].reshape([length, nj, 3])
@@ -150,10 +149,11 @@ def save_bvh(filename, positions, rotations, offsets, frametime=1.0 / 60.0, name
     for c in children[0]:
         joint(c, '\t')
     lines.append("}\nMOTION\nFrames: %i\nFrame Time: %f\n" % (len(rotations), frametime))
+    # motion block: "%f %f %f " per (root position, joint rotations in hierarchy order), one C-level format call per file
     rot_seq = rotations[:, seq, :]
-    for i in range(rotations.shape[0]):
-        row = "%f %f %f " % tuple(positions[i, 0]) + "".join("%f %f %f " % tuple(r) for r in rot_seq[i])
-        lines.append(row + "\n")
+    table = np.concatenate([positions[:, 0, :], rot_seq.reshape(rot_seq.shape[0], -1)], axis=1)
+    row_fmt = "%f " * table.shape[1] + "\n"
+    lines.append((row_fmt * table.shape[0]) % tuple(table.ravel().tolist()))
     with open(filename, 'w') as f:
         f.write("".join(lines))
 

@@ -11,7 +11,9 @@ Differences from the reference, all additive:
   * the WavLM-Large conditioning forward (``wavlm_init`` / ``wav2wavlm``, sample.py:28-48) runs in libdsg too
     (dsg_wavlm_forward) and takes all segments of a clip as one batch; conditioning may also be given as
     precomputed WavLM-shaped features;
-  * new optional YAML keys: ``precision`` (bf16|fp32), ``sampler`` (ddpm|ddim), ``timestep_respacing``.
+  * new optional YAML keys: ``precision`` (bf16|fp32), ``sampler`` (ddpm|ddim), ``timestep_respacing``, ``max_batch``;
+  * ``--batch manifest.csv`` (``main_batch``): many clips per run — wav load, style parsing, batched WavLM + sampling
+    of clips with equal segment counts, BVH files written by a thread pool.
 """
 import argparse
 import math
@@ -235,6 +237,103 @@ def main(args, save_dir, model_path, audio_path=None, mfcc_path=None, audiowavlm
                      minibatch=True, skip_timesteps=0, style=style, seed=123456, features=features, save_dir=save_dir)
 
 
+def read_manifest(path):
+    """Batch manifest (CSV, '#' comments, optional header `wav,style,clip_id`): one clip per row.
+    `style` = a name of `style2onehot`, an index 0..5, or empty -> token 1 of the file name (sample.py:378);
+    `clip_id` (optional) keys the clip's noise stream (default: the row number)."""
+    import csv
+    rows = []
+    with open(path, newline='') as fh:
+        for rec in csv.reader(fh):
+            rec = [c.strip() for c in rec]
+            if not rec or not rec[0] or rec[0].startswith('#') or rec[0].lower() in ('wav', 'wav_path', 'path'):
+                continue
+            wav = rec[0]
+            tok = rec[1] if len(rec) > 1 and rec[1] else os.path.basename(wav).split('_')[1]
+            if tok in style2onehot:
+                style = style2onehot[tok]
+            elif tok.isdigit() and int(tok) < 6:
+                style = [1 if i == int(tok) else 0 for i in range(6)]
+            else:
+                raise ValueError(f"{path}: unknown style '{tok}' for {wav}")
+            cid = int(rec[2]) if len(rec) > 2 and rec[2] else len(rows)
+            rows.append({'wav': wav, 'style': style, 'style_name': tok, 'clip_id': cid})
+    if not rows:
+        raise ValueError(f"{path}: empty manifest")
+    return rows
+
+
+def segment_windows(audio, n_frames, n_poses, n_seed):
+    """sample.py:224-251 for one clip: [nseg, n_poses * 800] waveform windows = the last n_seed frames of the previous
+    stride (zeros for the first) followed by the segment's own stride."""
+    nseg, n_frames = segment_plan(n_frames, n_poses, n_seed)
+    stride = n_poses - n_seed
+    chunks = torch.from_numpy(np.ascontiguousarray(audio[:int(n_frames * 16000 / 20)])).to(torch.float32).reshape(nseg, int(stride * 16000 / 20))
+    pad = int(n_seed * 16000 / 20)
+    return torch.stack([torch.cat((torch.zeros(pad) if i == 0 else chunks[i - 1, -pad:], chunks[i])) for i in range(nseg)]), n_frames
+
+
+def plan_batches(lengths, max_batch):
+    """Group clips with the same number of segments (they run in lock-step), at most max_batch per group.
+    lengths: segments per clip.  Returns a list of index lists, longest clips first."""
+    by = {}
+    for i, n in enumerate(lengths):
+        by.setdefault(n, []).append(i)
+    out = []
+    for n in sorted(by, reverse=True):
+        idx = by[n]
+        out += [idx[i:i + max_batch] for i in range(0, len(idx), max_batch)]
+    return out
+
+
+def main_batch(args, save_dir, model_path, manifest, max_len=0, wavlm_model=None, model=None, diffusion=None,
+               seed=123456, stats_path=DEFAULT_STATS, writers=8):
+    """Many clips at once (additive to the reference CLI): every clip of the manifest goes through WavLM and the sampler in
+    batches of clips with equal segment counts; BVH files are written by a thread pool while the GPU runs the next batch."""
+    from concurrent.futures import ThreadPoolExecutor
+    rows = read_manifest(manifest) if isinstance(manifest, str) else manifest
+    os.makedirs(save_dir, exist_ok=True)
+    dev = torch.device('cuda:' + str(_get(args, 'gpu', '0')))
+    max_batch = int(_get(args, 'max_batch', 148))
+    if model is None:
+        cfg = dict(args) if isinstance(args, dict) else dict(vars(args))
+        cfg['max_batch'] = max_batch
+        model, diffusion = create_model_and_diffusion(Config(cfg))
+        load_model_wo_clip(model, torch.load(model_path, map_location='cpu'))
+        model.to(dev).eval()
+    if wavlm_model is None:
+        wavlm_model = wavlm_init(dev, _get(args, 'wavlm_path', './WavLM/WavLM-Large.pt'))
+    g = model.geometry
+    sampler = _get(args, 'sampler', 'ddpm')
+    wins = []
+    for r in rows:
+        audio = r['audio'] if 'audio' in r else load_wav_16k(r['wav'])[0]
+        n_frames = max_len if max_len else audio.shape[0] * 20 // 16000
+        n_frames = min(n_frames, audio.shape[0] * 20 // 16000)
+        wins.append(segment_windows(audio, n_frames, g.n_poses, g.n_seed))
+    paths = [None] * len(rows)
+
+    def write(i, seq, n_frames):
+        r = rows[i]
+        name = os.path.splitext(os.path.basename(r['wav']))[0]
+        path = os.path.join(save_dir, f"{name}_{n_frames}_{r['style_name']}_{seed}_{r['clip_id']}.bvh")
+        pose2bvh(denormalise(seq, stats_path), path, length=n_frames - g.n_seed, smoothing=True)
+        paths[i] = path
+
+    with ThreadPoolExecutor(max_workers=writers) as pool:
+        jobs = []
+        for idx in plan_batches([w[0].shape[0] for w in wins], max_batch):
+            nseg = wins[idx[0]][0].shape[0]
+            feats = [wav2wavlm(wavlm_model, torch.stack([wins[i][0][s] for i in idx]), dev, g.n_poses) for s in range(nseg)]
+            styles = torch.tensor([rows[i]['style'] for i in idx], dtype=torch.float32)
+            seqs = inference_batch(model, diffusion, feats, styles, seed=seed, clip_ids=[rows[i]['clip_id'] for i in idx],
+                                   smoothing=True, sampler=sampler).numpy()
+            jobs += [pool.submit(write, i, seqs[k], wins[i][1]) for k, i in enumerate(idx)]
+        for j in jobs:
+            j.result()
+    return paths
+
+
 def parse_cli(argv=None):
     parser = argparse.ArgumentParser(description='DiffuseStyleGesture')
     parser.add_argument('--config', default=DEFAULT_CONFIG)
@@ -243,6 +342,9 @@ def parse_cli(argv=None):
     parser.add_argument('--model_path', type=str, default='./model000450000.pt')
     parser.add_argument('--audiowavlm_path', type=str, default='')
     parser.add_argument('--max_len', type=int, default=0)
+    parser.add_argument('--batch', type=str, default='', help='CSV manifest (wav,style[,clip_id]) -> one BVH per row (additive)')
+    parser.add_argument('--save_dir', type=str, default='sample_dir')
+    parser.add_argument('--wavlm_path', type=str, default='./WavLM/WavLM-Large.pt')
     args = parser.parse_args(argv)
     with open(args.config) as f:
         config = yaml.safe_load(f)
@@ -255,5 +357,9 @@ if __name__ == '__main__':
     config = parse_cli()
     pprint(dict(config))
     torch.cuda.set_device(int(config.gpu))
-    main(config, 'sample_dir', config.model_path, audio_path=None, mfcc_path=None,
-         audiowavlm_path=config.audiowavlm_path, max_len=config.max_len)
+    if config.batch:
+        for p in main_batch(config, config.save_dir, config.model_path, config.batch, max_len=config.max_len):
+            print(p)
+    else:
+        main(config, config.save_dir, config.model_path, audio_path=None, mfcc_path=None,
+             audiowavlm_path=config.audiowavlm_path, max_len=config.max_len)

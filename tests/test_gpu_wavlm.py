@@ -64,3 +64,36 @@ def test_wav_to_bvh_through_both_engines(tmp_path):
     w1 = torch.cat((a[0, -6400:], a[1]))[None]
     f01 = S.wav2wavlm(wm, torch.cat((w0, w1)), 'cuda:0', 88)
     assert torch.equal(f01[0], S.wav2wavlm(wm, w0, 'cuda:0', 88)[0]) and torch.equal(f01[1], S.wav2wavlm(wm, w1, 'cuda:0', 88)[0])
+
+
+def test_batch_manifest_matches_single_clip_runs(tmp_path):
+    """`sample.main_batch` (clips of different lengths, batched per segment count) gives every clip the result of running it
+    alone with the same clip id: batching changes nothing (counter-based noise; row-independent kernels)."""
+    from diffusestylegesture_b200 import sample as S
+    from diffusestylegesture_b200.config import ZEGGS
+    from diffusestylegesture_b200.mdm import MDM
+    from diffusestylegesture_b200.model_util import create_gaussian_diffusion, load_model_wo_clip
+    from diffusestylegesture_b200.synthetic import synthetic_state_dict
+    wm = WavLM(max_batch=4)
+    wm.load_state_dict(synthetic_wavlm_state_dict(WAVLM_LARGE, seed=0))
+    wm.to('cuda:0').eval()
+    model = MDM(njoints=ZEGGS.njoints, cond_mode='cross_local_attention3_style1', audio_feat='wavlm', n_seed=8, precision='bf16', max_batch=2)
+    load_model_wo_clip(model, synthetic_state_dict(ZEGGS, seed=0))
+    model.to('cuda:0').eval()
+    d = create_gaussian_diffusion([20])
+    wavs = synthetic_wav(3, 170 * 800).numpy()
+    rows = [{'wav': 'a_Happy_0.wav', 'style': [1, 0, 0, 0, 0, 0], 'style_name': 'Happy', 'clip_id': 0, 'audio': wavs[0]},
+            {'wav': 'b_Old_0.wav', 'style': [0, 0, 0, 1, 0, 0], 'style_name': 'Old', 'clip_id': 5, 'audio': wavs[1][:100 * 800]},
+            {'wav': 'c_Sad_0.wav', 'style': [0, 1, 0, 0, 0, 0], 'style_name': 'Sad', 'clip_id': 9, 'audio': wavs[2]}]
+    paths = S.main_batch(S.Config(n_poses=88, audio_feat="wavlm", gpu="0", max_batch=2), str(tmp_path), None, rows,
+                         wavlm_model=wm, model=model, diffusion=d, seed=7)
+    assert len(paths) == 3 and all(os.path.getsize(p) > 1e5 for p in paths)
+    frames = [int([l for l in open(p).read().splitlines() if l.startswith("Frames:")][0].split()[1]) for p in paths]
+    assert frames == [456, 216, 456]                                  # (160 - 8) * 3, (80 - 8) * 3
+    # clip 2 alone, same clip id
+    w, n_frames = S.segment_windows(wavs[2], 170, 88, 8)
+    feats = [S.wav2wavlm(wm, w[s:s + 1], 'cuda:0', 88) for s in range(2)]
+    seq = S.inference_batch(model, d, feats, torch.tensor([[0, 1, 0, 0, 0, 0]], dtype=torch.float32), seed=7, clip_ids=[9], smoothing=True)
+    single = str(tmp_path / "single.bvh")
+    S.pose2bvh(S.denormalise(seq[0].numpy()), single, length=n_frames - 8, smoothing=True)
+    assert open(single).read() == open(paths[2]).read()

@@ -186,3 +186,44 @@ def test_world_size_2_gather_gloo(tmp_path):
                        capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "GATHER_OK" in r.stdout
+
+
+def test_manifest_windows_and_batch_plan(tmp_path):
+    """Batch front-end: manifest parsing, per-clip waveform windows (sample.py:224-251), batch plan."""
+    from diffusestylegesture_b200 import sample as S
+    man = tmp_path / "m.csv"
+    man.write_text("wav,style,clip_id\n# comment\n/a/015_Happy_4_x_1_0.wav\n/a/b.wav,Old\n/a/c.wav,4,17\n")
+    rows = S.read_manifest(str(man))
+    assert [r["style"] for r in rows] == [[1, 0, 0, 0, 0, 0], [0, 0, 0, 1, 0, 0], [0, 0, 0, 0, 1, 0]]
+    assert [r["clip_id"] for r in rows] == [0, 1, 17]
+    man.write_text("/a/x_Bogus_1.wav\n")
+    with pytest.raises(ValueError):
+        S.read_manifest(str(man))
+    audio = np.arange(170 * 800, dtype=np.float32)
+    w, n_frames = S.segment_windows(audio, 170, 88, 8)
+    assert w.shape == (2, 70400) and n_frames == 160
+    assert float(w[0, :6400].abs().max()) == 0.0 and float(w[0, 6400]) == 0.0 and float(w[0, -1]) == 80 * 800 - 1
+    assert float(w[1, 0]) == 80 * 800 - 6400 and float(w[1, -1]) == 160 * 800 - 1       # 8 seed frames of the previous stride
+    assert S.plan_batches([4, 2, 4, 1, 2, 4], 2) == [[0, 2], [5], [1, 4], [3]]
+    assert S.segment_plan(50, 88, 8) == (1, 50)
+
+
+def test_bvh_writer_is_vectorised_and_stable(tmp_path):
+    """One C-level format call per file and one savgol call per clip: same text as the per-row / per-column reference loops."""
+    from scipy.signal import savgol_filter
+    from diffusestylegesture_b200 import process_zeggs_bvh as PB
+    from diffusestylegesture_b200.sample import denormalise
+    rng = np.random.default_rng(3)
+    poses = denormalise(rng.standard_normal((40, 1141)).astype(np.float32) * 0.1)
+    pos, eul = PB.pose2bvh_arrays(poses, 40, smoothing=True)
+    loop = np.stack([savgol_filter(poses[:, c], 15, 2) for c in range(poses.shape[1])], 1)
+    pos2, eul2 = PB.pose2bvh_arrays(loop, 40, smoothing=False)
+    assert np.abs(pos - pos2).max() < 1e-9 and np.abs(eul - eul2).max() < 1e-7
+    path = str(tmp_path / "a.bvh")
+    PB.pose2bvh(poses, path, 40, smoothing=True)
+    lines = open(path).read().splitlines()
+    k = lines.index("MOTION")
+    assert lines[k + 1] == "Frames: 120" and len(lines) == k + 3 + 120
+    row = lines[k + 3].split(" ")
+    assert len(row) == 3 + 75 * 3 + 1 and row[-1] == ""                           # "%f " per value, trailing space
+    assert abs(float(row[0]) - pos[0, 0, 0]) < 1e-6
