@@ -255,9 +255,10 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
           }
           for (int l = 0; l < NL; ++l) {
             const int rb = l * R_LAYER;
-            for (int h = 0; h < NH; ++h)
-              for (int part = 0; part < 3; ++part)
-                for (int kb = 0; kb < 4; ++kb) load(&tm_w64, rb + R_QKV + h * 192 + part * 64, kb * 64, WSTAGE / 2);
+            for (int h = 0; h < NH; ++h) {              // per head: q|k rows as one 128-row box, v as a 64-row box
+              for (int kb = 0; kb < 4; ++kb) load(&tm_w128, rb + R_QKV + h * 192, kb * 64, WSTAGE);
+              for (int kb = 0; kb < 4; ++kb) load(&tm_w64, rb + R_QKV + h * 192 + 128, kb * 64, WSTAGE / 2);
+            }
             for (int nh = 0; nh < 2; ++nh)
               for (int kb = 0; kb < 4; ++kb) load(&tm_w128, rb + R_WO + nh * 128, kb * 64, WSTAGE);
             auto ff1 = [&](int c) { for (int kb = 0; kb < 4; ++kb) load(&tm_w128, rb + R_W1 + c * 128, kb * 64, WSTAGE); };
@@ -333,8 +334,8 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
               const int hb = h & 1;
               owait(B_ACCF + 2 * hb); owait(B_ACCF + 2 * hb + 1);
               tcgen05_fence_after();
-              for (int part = 0; part < 3; ++part)
-                for (int kb = 0; kb < 4; ++kb) tile(xs_addr + kb * KT, hb * 256 + part * 64, idesc64, kb > 0);
+              for (int kb = 0; kb < 4; ++kb) tile(xs_addr + kb * KT, hb * 256, idesc128, kb > 0);            // q | k
+              for (int kb = 0; kb < 4; ++kb) tile(xs_addr + kb * KT, hb * 256 + 128, idesc64, kb > 0);      // v
               tcgen05_commit(&bars[B_ACCR + 2 * hb]); tcgen05_commit(&bars[B_ACCR + 2 * hb + 1]);
             }
             // ---- out_proj: A = attention output in BUF, D = Q0|Q1
