@@ -262,11 +262,13 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
             for (int nh = 0; nh < 2; ++nh)
               for (int kb = 0; kb < 4; ++kb) load(&tm_w128, rb + R_WO + nh * 128, kb * 64, WSTAGE);
             auto ff1 = [&](int c) { for (int kb = 0; kb < 4; ++kb) load(&tm_w128, rb + R_W1 + c * 128, kb * 64, WSTAGE); };
+            // linear1 chunk c+2 goes BEFORE linear2 chunk c: it only needs GELU(c) to have read its accumulator (early),
+            // so the tensor core and the weight stream keep running while GELU(c) computes
             ff1(0); ff1(1);
             for (int c = 0; c < 8; ++c) {
+              if (c + 2 < 8) ff1(c + 2);
               for (int nh = 0; nh < 2; ++nh)
                 for (int kb2 = 0; kb2 < 2; ++kb2) load(&tm_w2, l * 256 + nh * 128, c * 128 + kb2 * 64, WSTAGE);
-              if (c + 2 < 8) ff1(c + 2);
             }
           }
           // pose head: weights + the x_t / z chunks the posterior needs (BUF is free once the last linear2 has completed)
@@ -357,13 +359,13 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
             };
             ff1(0); ff1(1);
             for (int c = 0; c < 8; ++c) {
+              if (c + 2 < 8) ff1(c + 2);                 // before linear2(c): see the producer
               owait(B_BUFR + (c & 1));
               if (c == 0) { owait(B_ACCF + 0); owait(B_ACCF + 1); }
               tcgen05_fence_after();
               for (int nh = 0; nh < 2; ++nh)
                 for (int kb2 = 0; kb2 < 2; ++kb2) tile(buf_addr + ((c & 1) * 2 + kb2) * KT, nh * 128, idesc128h, c > 0 || kb2 > 0);
               tcgen05_commit(&bars[B_BUFF + (c & 1)]);
-              if (c + 2 < 8) ff1(c + 2);
             }
             tcgen05_commit(&bars[B_ACCR + 0]); tcgen05_commit(&bars[B_ACCR + 1]);
             if (l == NL - 1) tcgen05_commit(&bars[B_HGO]);      // every read of BUF by the tensor core is complete
