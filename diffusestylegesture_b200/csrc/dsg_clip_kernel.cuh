@@ -24,21 +24,21 @@ namespace clip {
 using namespace tc;
 
 constexpr int D = 256, F = 1024, NH = 4, HD = 64, LH = 8, LHD = 32, WIN = 11, T = 88, S = 89, J = 1141, JPAD = 1152, NL = 8;
-constexpr int NS = 3;                       // weight ring stages
+constexpr int NS = 4;                       // weight ring stages: 3 at OFF_W + the token-less rows 96..127 of XS (16 KB)
 constexpr int WSTAGE = 16384;               // [128 rows x 64 k] bf16
 constexpr int KT = 16384;                   // one A k-tile [128 x 64] bf16
 constexpr int OFF_XS = 0;
 constexpr int OFF_BUF = 4 * KT;
 constexpr int OFF_W = 8 * KT;
 constexpr int QLD = 72;                     // Qs/Ks/Vs row stride (bf16 elements): 16 B pad -> conflict-free ldmatrix
-constexpr int OFF_Q = OFF_W + NS * WSTAGE;
+constexpr int OFF_Q = OFF_W + 3 * WSTAGE;
+constexpr int OFF_W3 = OFF_XS + 12 * 4096;      // 4th weight stage (see xs_off: XS is stored row-group-major)
 constexpr int OFF_K = OFF_Q + 96 * QLD * 2;
 constexpr int OFF_V = OFF_K + 96 * QLD * 2;
 constexpr int OFF_RED = OFF_V + 96 * QLD * 2;
-constexpr int OFF_B1 = OFF_RED + 2048;           // per-layer parameters staged in shared memory: b1[1024] fp16 | 2 KB spare | fp32 bq[256] | bo'[256] | b2[256]
-constexpr int OFF_LNP = OFF_XS + 12288;          // rows 96..127 of XS k-tile 0 (never a token): fp32 g1[256] | be1[256] | g2[256] | be2[256]
-constexpr int OFF_BOUT0 = OFF_XS + KT + 12288;   // same rows of k-tile 1: pose-head bias [0, 1024); k-tile 2: [1024, 1152)
-constexpr int OFF_BOUT1 = OFF_XS + 2 * KT + 12288;
+constexpr int OFF_B1 = OFF_RED + 2048;           // per-layer parameters (7 KB): b1[1024] fp16 | fp32 bq[256] | bo'[256] | b2[256] | 512 B | LayerNorm partials 1.5 KB;
+                                                 // during the pose head its first 4.5 KB hold the head bias instead
+constexpr int OFF_LNP = OFF_BUF + 12288;         // rows 96..127 of BUF k-tile 0 (never a token; free while the layers run): fp32 g1 | be1 | g2 | be2
 // pose-head phase: x_t / z chunks of 32 joint channels ([32][88] fp32 = 11,264 B each) are bulk-copied into 4 slots carved out
 // of BUF and the (idle) attention staging area
 constexpr int HCH = 32, HBYTES = HCH * T * 4, NHS = 4, NCHUNK = JPAD / HCH;
@@ -57,8 +57,8 @@ constexpr int P_BQKV = 0, P_BO = 768, P_G1 = 1024, P_BE1 = 1280, P_B1 = 1536, P_
 constexpr int R_LAYER = 2048, R_QKV = 0, R_WO = 768, R_W1 = 1024, R_HEAD = NL * R_LAYER;
 
 // barrier indices
-enum { B_WFULL = 0, B_WEMPTY = 3, B_AFULL = 6, B_AEMPTY = 10, B_ACCR = 14, B_ACCF = 18, B_XSR = 22, B_BUFR = 23, B_BUFF = 25,
-       B_ZR = 27, B_ZF = 28, B_HFULL = 29, B_HEMPTY = 33, B_HGO = 37, B_XAR = 38, B_COUNT = 39 };
+enum { B_WFULL = 0, B_WEMPTY = 4, B_AFULL = 8, B_AEMPTY = 12, B_ACCR = 16, B_ACCF = 20, B_XSR = 24, B_BUFR = 25, B_BUFF = 27,
+       B_ZR = 29, B_ZF = 30, B_HFULL = 31, B_HEMPTY = 35, B_HGO = 39, B_XAR = 40, B_COUNT = 41 };
 
 struct ClipParams {
   float* x;                 // [B][J][T] fp32, in/out
@@ -110,6 +110,21 @@ DSG_DEVINL void ldsm_x2(uint32_t& r0, uint32_t& r1, const void* p) {
 DSG_DEVINL uint32_t a_off(int r, int c) {
   return (uint32_t)((c >> 6) * KT + (r >> 3) * 1024 + (r & 7) * 128 + ((((c & 63) >> 3) ^ (r & 7)) << 4) + (c & 7) * 2);
 }
+// XS is stored row-group-major: 8-row group g of k-tile kt at g * 4096 + kt * 1024 (UMMA descriptors: SBO = 4096), so that the
+// token-less rows 96..127 of all four k-tiles form one contiguous 16 KB block — the 4th weight stage
+DSG_DEVINL uint32_t xs_off(int r, int c) {
+  return (uint32_t)((r >> 3) * 4096 + (c >> 6) * 1024 + (r & 7) * 128 + ((((c & 63) >> 3) ^ (r & 7)) << 4) + (c & 7) * 2);
+}
+DSG_DEVINL uint64_t make_sw128_desc_sbo(uint32_t smem_addr, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(sbo >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+DSG_DEVINL int wstage_off(int slot) { return slot < 3 ? OFF_W + slot * WSTAGE : OFF_W3; }
 DSG_DEVINL uint4 pack8(const float* v) {
   uint4 u;
   u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]); u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
@@ -224,7 +239,7 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
   if (q4 == 3 && sub == 0) {
     // =================================================== TMA weight producer ===================================================
     if (lane == 0) {
-      Phases ph{(0x7ull << B_WEMPTY) | (0xFull << B_AEMPTY) | (0xFull << B_HEMPTY)};     // "empty" barriers start free
+      Phases ph{(((1ull << NS) - 1) << B_WEMPTY) | (0xFull << B_AEMPTY) | (0xFull << B_HEMPTY)};     // "empty" barriers start free
       int slot = 0;
       long long t_wait = 0;
       const bool prof = PROF && P.prof != nullptr && blockIdx.x == 0;
@@ -233,7 +248,7 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
         ph.wait(bars, B_WEMPTY + slot);
         if (prof) t_wait += clock64() - c0;
         mbar_expect_tx(&bars[B_WFULL + slot], bytes);
-        tma_load_2d(smem + OFF_W + slot * WSTAGE, m, &bars[B_WFULL + slot], kcol, row);
+        tma_load_2d(smem + wstage_off(slot), m, &bars[B_WFULL + slot], kcol, row);
         slot = (slot + 1 == NS) ? 0 : slot + 1;
       };
       bool first = true;
@@ -298,21 +313,21 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
     if (lane == 0) {
       Phases ph{(0xFull << B_ACCF)};               // accumulators start free
       int slot = 0;
-      const uint32_t xs_addr = smem_u32(smem + OFF_XS), buf_addr = smem_u32(smem + OFF_BUF), w_addr = smem_u32(smem + OFF_W);
+      const uint32_t xs_addr = smem_u32(smem + OFF_XS), buf_addr = smem_u32(smem + OFF_BUF), smem_addr0 = smem_u32(smem);
       constexpr uint32_t idesc128 = make_idesc_bf16(128, 128), idesc64 = make_idesc_bf16(128, 64), idesc128h = make_idesc_f16(128, 128);
       // one weight tile: 4 UMMAs (K = 64) of A k-tile `a_tile` against the current stage
       long long t_w = 0, t_o = 0;
       const bool prof = PROF && P.prof != nullptr && blockIdx.x == 0;
       const long long t_begin = clock64();
-      auto tile = [&](uint32_t a_tile, uint32_t d_col, uint32_t idesc, bool acc_first) {
+      auto tile = [&](uint32_t a_tile, uint32_t d_col, uint32_t idesc, bool acc_first, uint32_t a_sbo = 1024) {
         const long long c0 = prof ? clock64() : 0;
         ph.wait(bars, B_WFULL + slot);
         if (prof) t_w += clock64() - c0;
         tcgen05_fence_after();
-        const uint32_t b_tile = w_addr + slot * WSTAGE;
+        const uint32_t b_tile = smem_addr0 + wstage_off(slot);
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk)
-          umma_bf16(tmem + d_col, make_sw128_desc(a_tile + kk * 32), make_sw128_desc(b_tile + kk * 32), idesc, (acc_first || kk > 0) ? 1u : 0u);
+          umma_bf16(tmem + d_col, make_sw128_desc_sbo(a_tile + kk * 32, a_sbo), make_sw128_desc(b_tile + kk * 32), idesc, (acc_first || kk > 0) ? 1u : 0u);
         tcgen05_commit(&bars[B_WEMPTY + slot]);
         slot = (slot + 1 == NS) ? 0 : slot + 1;
       };
@@ -336,8 +351,8 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
               const int hb = h & 1;
               owait(B_ACCF + 2 * hb); owait(B_ACCF + 2 * hb + 1);
               tcgen05_fence_after();
-              for (int kb = 0; kb < 4; ++kb) tile(xs_addr + kb * KT, hb * 256, idesc128, kb > 0);            // q | k
-              for (int kb = 0; kb < 4; ++kb) tile(xs_addr + kb * KT, hb * 256 + 128, idesc64, kb > 0);      // v
+              for (int kb = 0; kb < 4; ++kb) tile(xs_addr + kb * 1024, hb * 256, idesc128, kb > 0, 4096);            // q | k
+              for (int kb = 0; kb < 4; ++kb) tile(xs_addr + kb * 1024, hb * 256 + 128, idesc64, kb > 0, 4096);      // v
               tcgen05_commit(&bars[B_ACCR + 2 * hb]); tcgen05_commit(&bars[B_ACCR + 2 * hb + 1]);
             }
             // ---- out_proj: A = attention output in BUF, D = Q0|Q1
@@ -354,7 +369,7 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
             auto ff1 = [&](int c) {
               owait(B_ACCF + 2 + (c & 1));
               tcgen05_fence_after();
-              for (int kb = 0; kb < 4; ++kb) tile(xs_addr + kb * KT, (2 + (c & 1)) * 128, idesc128, kb > 0);
+              for (int kb = 0; kb < 4; ++kb) tile(xs_addr + kb * 1024, (2 + (c & 1)) * 128, idesc128, kb > 0, 4096);
               tcgen05_commit(&bars[B_ACCR + 2 + (c & 1)]);
             };
             ff1(0); ff1(1);
@@ -376,7 +391,7 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
           for (int t = 0; t < JPAD / 128; ++t) {
             owait(B_ACCF + (t & 3));
             tcgen05_fence_after();
-            for (int kb = 0; kb < 4; ++kb) tile(xs_addr + kb * KT, (t & 3) * 128, idesc128, kb > 0);
+            for (int kb = 0; kb < 4; ++kb) tile(xs_addr + kb * 1024, (t & 3) * 128, idesc128, kb > 0, 4096);
             tcgen05_commit(&bars[B_ACCR + (t & 3)]);
           }
         }
@@ -414,7 +429,7 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
     __nv_bfloat16* Ks = reinterpret_cast<__nv_bfloat16*>(smem + OFF_K);
     __nv_bfloat16* Vs = reinterpret_cast<__nv_bfloat16*>(smem + OFF_V);
     float* red_s = reinterpret_cast<float*>(smem + OFF_RED);            // [4][96] row sums
-    float* red_q = reinterpret_cast<float*>(smem + OFF_B1 + 2048);      // [4][96] row sums of squares
+    float* red_q = reinterpret_cast<float*>(smem + OFF_B1 + 5632);      // [4][96] row sums of squares
     float* b1s = reinterpret_cast<float*>(smem + OFF_B1);
     float* lnp = reinterpret_cast<float*>(smem + OFF_LNP);
     uint8_t* XS = smem + OFF_XS;
@@ -454,7 +469,7 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         float rs[8];
-        unpack8(*reinterpret_cast<const uint4*>(XS + a_off(r, col0 + i * 8)), rs);
+        unpack8(*reinterpret_cast<const uint4*>(XS + xs_off(r, col0 + i * 8)), rs);
         const float4 b0 = *reinterpret_cast<const float4*>(bias + col0 + i * 8);
         const float4 b1 = *reinterpret_cast<const float4*>(bias + col0 + i * 8 + 4);
         v[i * 8 + 0] += rs[0] + b0.x; v[i * 8 + 1] += rs[1] + b0.y; v[i * 8 + 2] += rs[2] + b0.z; v[i * 8 + 3] += rs[3] + b0.w;
@@ -476,7 +491,7 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
         v[i + 2] = (v[i + 2] - mean) * rstd * g4.z + b4.z; v[i + 3] = (v[i + 3] - mean) * rstd * g4.w + b4.w;
       }
 #pragma unroll
-      for (int i = 0; i < 8; ++i) *reinterpret_cast<uint4*>(XS + a_off(r, col0 + i * 8)) = pack8(v + i * 8);
+      for (int i = 0; i < 8; ++i) *reinterpret_cast<uint4*>(XS + xs_off(r, col0 + i * 8)) = pack8(v + i * 8);
       fence_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars[B_XSR]);
@@ -490,14 +505,12 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
         float* o = P.dbg + (long long)slot * P.dbg_slot + ((long long)clip * S + r) * D + sub * 64;
         for (int c8 = 0; c8 < 8; ++c8) {
           float t8[8];
-          unpack8(*reinterpret_cast<const uint4*>(XS + a_off(r, sub * 64 + c8 * 8)), t8);
+          unpack8(*reinterpret_cast<const uint4*>(XS + xs_off(r, sub * 64 + c8 * 8)), t8);
           for (int i = 0; i < 8; ++i) o[c8 * 8 + i] = t8[i];
         }
       }
     };
 
-    for (int i = wt; i < JPAD; i += NWT)               // pose-head bias -> token-less rows of XS k-tiles 1 and 2
-      *reinterpret_cast<float*>(smem + (i < 1024 ? OFF_BOUT0 + i * 4 : OFF_BOUT1 + (i - 1024) * 4)) = __ldg(P.bout + i);
     for (int clip = blockIdx.x; clip < P.B; clip += gridDim.x) {
       float* xc = P.x + (long long)clip * J * T;
       uint8_t* xac = P.xa + (long long)clip * XA_BYTES;
@@ -621,14 +634,14 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
                 ol[e] = a * cs.x - b * cs.y;
                 oh[e] = b * cs.x + a * cs.y;
               }
-              *reinterpret_cast<uint32_t*>(XS + a_off(pos, lh * 32 + dt * 8 + t2)) = pack_bf16x2(ol[0], ol[1]);
-              *reinterpret_cast<uint32_t*>(XS + a_off(pos, lh * 32 + 16 + dt * 8 + t2)) = pack_bf16x2(oh[0], oh[1]);
+              *reinterpret_cast<uint32_t*>(XS + xs_off(pos, lh * 32 + dt * 8 + t2)) = pack_bf16x2(ol[0], ol[1]);
+              *reinterpret_cast<uint32_t*>(XS + xs_off(pos, lh * 32 + 16 + dt * 8 + t2)) = pack_bf16x2(oh[0], oh[1]);
             }
           }
         }
         if (wt < D) {   // token row: tok = emb_1 + emb_t (rotary at position 0 is the identity)
           const float tv = __ldg(P.emb1 + (long long)clip * D + wt) + __ldg(P.te + (long long)trow * D + wt);
-          *reinterpret_cast<__nv_bfloat16*>(XS + a_off(0, wt)) = __float2bfloat16_rn(tv);
+          *reinterpret_cast<__nv_bfloat16*>(XS + xs_off(0, wt)) = __float2bfloat16_rn(tv);
         }
         fence_async_smem();
         workers_sync();                                  // Z staging (BUF) is dead from here on
@@ -649,11 +662,11 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
               reinterpret_cast<float4*>(lnp)[i] = __ldg(reinterpret_cast<const float4*>(lp + ((i >> 7) ? P_G2 : P_G1)) + (i & 127));
             } else if (i < 320) {                        // q bias (per head, [h][64]); the k bias drops out of the softmax,
               const int j = i - 256, h = j >> 4, i4 = j & 15;   // the v bias is folded into bo' = bo + Wo bv at set-up
-              reinterpret_cast<float4*>(b1s + 1024)[j] = __ldg(reinterpret_cast<const float4*>(lp + P_BQKV + h * 192) + i4);
+              reinterpret_cast<float4*>(b1s + 512)[j] = __ldg(reinterpret_cast<const float4*>(lp + P_BQKV + h * 192) + i4);
             } else if (i < 384) {
-              reinterpret_cast<float4*>(b1s + 1280)[i - 320] = __ldg(reinterpret_cast<const float4*>(lp + P_BO) + (i - 320));
+              reinterpret_cast<float4*>(b1s + 768)[i - 320] = __ldg(reinterpret_cast<const float4*>(lp + P_BO) + (i - 320));
             } else {
-              reinterpret_cast<float4*>(b1s + 1536)[i - 384] = __ldg(reinterpret_cast<const float4*>(lp + P_B2) + (i - 384));
+              reinterpret_cast<float4*>(b1s + 1024)[i - 384] = __ldg(reinterpret_cast<const float4*>(lp + P_B2) + (i - 384));
             }
           }
           workers_sync();
@@ -676,7 +689,7 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
                 __nv_bfloat16* dst = (ch < 4 ? Qs : (ch < 8 ? Ks : Vs)) + r * QLD + (ch & 3) * 16;
                 if (r < S) {
                   if (ch < 4) {
-                    const float* bq = b1s + 1024 + h * 64 + ch * 16;
+                    const float* bq = b1s + 512 + h * 64 + ch * 16;
 #pragma unroll
                     for (int i = 0; i < 16; i += 4) {
                       const float4 b4 = *reinterpret_cast<const float4*>(bq + i);
@@ -791,7 +804,7 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
             if (hb == 1 && lane == 0) mbar_arrive(&bars[B_BUFR + (h >> 1)]);
             lap(PF_W_ATT);
           }
-          layernorm_epilogue(b1s + 1280, lnp, lnp + 256);
+          layernorm_epilogue(b1s + 768, lnp, lnp + 256);
           // ---- FFN: GELU epilogue per 128-unit chunk -> BUF half (c & 1) as the (fp16) A operand of linear2
           for (int c = 0; c < 8; ++c) {
             const int qd = 2 + (c & 1);
@@ -822,12 +835,15 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
             if (lane == 0) mbar_arrive(&bars[B_BUFR + (c & 1)]);
             lap(PF_W_GELU);
           }
-          layernorm_epilogue(b1s + 1536, lnp + 512, lnp + 768);
+          layernorm_epilogue(b1s + 1024, lnp + 512, lnp + 768);
           debug_dump(l + 1, clip);
         }
 
         // ---------------- pose head + posterior: x <- f(x0, x, z) in place (fp32, global) and as next step's bf16 A k-blocks.
         // Chunk c = 32 joint channels (TMEM quarter (c >> 2) & 3, columns (c & 3) * 32); the four column quarters take 8 each.
+        // the layer parameters are dead (every warp is past the barrier of the last LayerNorm): the head bias takes their place
+        for (int i = wt; i < JPAD; i += NWT) b1s[i] = __ldg(P.bout + i);
+        workers_sync();
         lap(PF_W_ZWAIT);
         {
           const float4 cf = P.coef[index];
@@ -846,7 +862,7 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
             if (ok && j0 < J) {
               const float* xs = reinterpret_cast<const float*>(smem + hslot_x(sl)) + sub * 8 * T + f;
               const float* zs = reinterpret_cast<const float*>(smem + hslot_z(sl)) + sub * 8 * T + f;
-              const float* bo = reinterpret_cast<const float*>(smem + (j0 < 1024 ? OFF_BOUT0 + j0 * 4 : OFF_BOUT1 + (j0 - 1024) * 4));
+              const float* bo = b1s + j0;
               float* xg = xc + (long long)j0 * T + f;
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
