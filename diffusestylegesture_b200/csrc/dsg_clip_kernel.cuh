@@ -11,7 +11,7 @@
 // Tensor memory (512 columns) = 4 quarters of 128 fp32 columns (Q0..Q3), handed back and forth per op with
 // ready/free mbarriers.  Shared memory:
 //   XS  [128 x 256] bf16, UMMA K-major SWIZZLE_128B (4 k-tiles)  — the residual stream AND the A operand; rows 96..127
-//                                        carry no token, so k-tile 0's 4 KB there holds the layer's LayerNorm gains/biases
+//                                        carry no token, so k-tile 0's rows 96..127 form the 4th weight stage
 //   BUF [128 x 256] bf16, same format — A ring of the input GEMM / rope'd h for local attention /
 //                                        attention output (A of out_proj) / FFN hidden chunk (fp16, A of linear2)
 //   W   3 x 16 KB weight stages ([128 or 64 rows] x 64 k), TMA + mbarrier ring
@@ -24,7 +24,7 @@ namespace clip {
 using namespace tc;
 
 constexpr int D = 256, F = 1024, NH = 4, HD = 64, LH = 8, LHD = 32, WIN = 11, T = 88, S = 89, J = 1141, JPAD = 1152, NL = 8;
-constexpr int NS = 3;                       // weight ring stages: 3 at OFF_W + the token-less rows 96..127 of XS (16 KB)
+constexpr int NS = 4;                       // weight ring stages: 3 at OFF_W + the token-less rows 96..127 of XS (16 KB)
 constexpr int WSTAGE = 16384;               // [128 rows x 64 k] bf16
 constexpr int KT = 16384;                   // one A k-tile [128 x 64] bf16
 constexpr int OFF_XS = 0;
@@ -38,7 +38,7 @@ constexpr int OFF_V = OFF_K + 96 * QLD * 2;
 constexpr int OFF_RED = OFF_V + 96 * QLD * 2;
 constexpr int OFF_B1 = OFF_RED + 2048;           // per-layer parameters (7 KB): b1[1024] fp16 | fp32 bq[256] | bo'[256] | b2[256] | 512 B | LayerNorm partials 1.5 KB;
                                                  // during the pose head its first 4.5 KB hold the head bias instead
-constexpr int OFF_LNP = OFF_BUF + 12288;         // rows 96..127 of BUF k-tile 0 (never a token; free while the layers run): fp32 g1 | be1 | g2 | be2
+constexpr int OFF_LNP = OFF_BUF + 3 * KT + 12288; // rows 96..127 of BUF k-tile 3: never a token, and beyond the pose-head chunk slots (which start landing before the last LayerNorm ends): fp32 g1 | be1 | g2 | be2
 // pose-head phase: x_t / z chunks of 32 joint channels ([32][88] fp32 = 11,264 B each) are bulk-copied into 4 slots carved out
 // of BUF and the (idle) attention staging area
 constexpr int HCH = 32, HBYTES = HCH * T * 4, NHS = 4, NCHUNK = JPAD / HCH;
@@ -351,8 +351,8 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
               const int hb = h & 1;
               owait(B_ACCF + 2 * hb); owait(B_ACCF + 2 * hb + 1);
               tcgen05_fence_after();
-              for (int kb = 0; kb < 4; ++kb) tile(xs_addr + kb * KT, hb * 256, idesc128, kb > 0);            // q | k
-              for (int kb = 0; kb < 4; ++kb) tile(xs_addr + kb * KT, hb * 256 + 128, idesc64, kb > 0);      // v
+              for (int kb = 0; kb < 4; ++kb) tile(xs_addr + kb * 1024, hb * 256, idesc128, kb > 0, 4096);            // q | k
+              for (int kb = 0; kb < 4; ++kb) tile(xs_addr + kb * 1024, hb * 256 + 128, idesc64, kb > 0, 4096);      // v
               tcgen05_commit(&bars[B_ACCR + 2 * hb]); tcgen05_commit(&bars[B_ACCR + 2 * hb + 1]);
             }
             // ---- out_proj: A = attention output in BUF, D = Q0|Q1
@@ -369,7 +369,7 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
             auto ff1 = [&](int c) {
               owait(B_ACCF + 2 + (c & 1));
               tcgen05_fence_after();
-              for (int kb = 0; kb < 4; ++kb) tile(xs_addr + kb * KT, (2 + (c & 1)) * 128, idesc128, kb > 0);
+              for (int kb = 0; kb < 4; ++kb) tile(xs_addr + kb * 1024, (2 + (c & 1)) * 128, idesc128, kb > 0, 4096);
               tcgen05_commit(&bars[B_ACCR + 2 + (c & 1)]);
             };
             ff1(0); ff1(1);
@@ -391,7 +391,7 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
           for (int t = 0; t < JPAD / 128; ++t) {
             owait(B_ACCF + (t & 3));
             tcgen05_fence_after();
-            for (int kb = 0; kb < 4; ++kb) tile(xs_addr + kb * KT, (t & 3) * 128, idesc128, kb > 0);
+            for (int kb = 0; kb < 4; ++kb) tile(xs_addr + kb * 1024, (t & 3) * 128, idesc128, kb > 0, 4096);
             tcgen05_commit(&bars[B_ACCR + (t & 3)]);
           }
         }
@@ -468,7 +468,7 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         float rs[8];
-        unpack8(*reinterpret_cast<const uint4*>(XS + a_off(r, col0 + i * 8)), rs);
+        unpack8(*reinterpret_cast<const uint4*>(XS + xs_off(r, col0 + i * 8)), rs);
         const float4 b0 = *reinterpret_cast<const float4*>(bias + col0 + i * 8);
         const float4 b1 = *reinterpret_cast<const float4*>(bias + col0 + i * 8 + 4);
         v[i * 8 + 0] += rs[0] + b0.x; v[i * 8 + 1] += rs[1] + b0.y; v[i * 8 + 2] += rs[2] + b0.z; v[i * 8 + 3] += rs[3] + b0.w;
@@ -490,7 +490,7 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
         v[i + 2] = (v[i + 2] - mean) * rstd * g4.z + b4.z; v[i + 3] = (v[i + 3] - mean) * rstd * g4.w + b4.w;
       }
 #pragma unroll
-      for (int i = 0; i < 8; ++i) *reinterpret_cast<uint4*>(XS + a_off(r, col0 + i * 8)) = pack8(v + i * 8);
+      for (int i = 0; i < 8; ++i) *reinterpret_cast<uint4*>(XS + xs_off(r, col0 + i * 8)) = pack8(v + i * 8);
       fence_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars[B_XSR]);
@@ -504,7 +504,7 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
         float* o = P.dbg + (long long)slot * P.dbg_slot + ((long long)clip * S + r) * D + sub * 64;
         for (int c8 = 0; c8 < 8; ++c8) {
           float t8[8];
-          unpack8(*reinterpret_cast<const uint4*>(XS + a_off(r, sub * 64 + c8 * 8)), t8);
+          unpack8(*reinterpret_cast<const uint4*>(XS + xs_off(r, sub * 64 + c8 * 8)), t8);
           for (int i = 0; i < 8; ++i) o[c8 * 8 + i] = t8[i];
         }
       }
@@ -633,14 +633,14 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
                 ol[e] = a * cs.x - b * cs.y;
                 oh[e] = b * cs.x + a * cs.y;
               }
-              *reinterpret_cast<uint32_t*>(XS + a_off(pos, lh * 32 + dt * 8 + t2)) = pack_bf16x2(ol[0], ol[1]);
-              *reinterpret_cast<uint32_t*>(XS + a_off(pos, lh * 32 + 16 + dt * 8 + t2)) = pack_bf16x2(oh[0], oh[1]);
+              *reinterpret_cast<uint32_t*>(XS + xs_off(pos, lh * 32 + dt * 8 + t2)) = pack_bf16x2(ol[0], ol[1]);
+              *reinterpret_cast<uint32_t*>(XS + xs_off(pos, lh * 32 + 16 + dt * 8 + t2)) = pack_bf16x2(oh[0], oh[1]);
             }
           }
         }
         if (wt < D) {   // token row: tok = emb_1 + emb_t (rotary at position 0 is the identity)
           const float tv = __ldg(P.emb1 + (long long)clip * D + wt) + __ldg(P.te + (long long)trow * D + wt);
-          *reinterpret_cast<__nv_bfloat16*>(XS + a_off(0, wt)) = __float2bfloat16_rn(tv);
+          *reinterpret_cast<__nv_bfloat16*>(XS + xs_off(0, wt)) = __float2bfloat16_rn(tv);
         }
         fence_async_smem();
         workers_sync();                                  // Z staging (BUF) is dead from here on
@@ -651,9 +651,8 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
         // ---------------- transformer layers
         for (int l = 0; l < NL; ++l) {
           const float* lp = P.lparams + (long long)l * P_SIZE;
-          // LayerNorm gains / biases alternate between the token-less rows of BUF k-tiles 0 and 1: a warp that is already past
-          // the last barrier of layer l-1's LayerNorm may stage layer l while slower warps still read layer l-1's
-          float* lnp = reinterpret_cast<float*>(smem + OFF_LNP + (l & 1) * KT);
+          float* lnp = reinterpret_cast<float*>(smem + OFF_LNP);
+          workers_sync();                                // every warp is done with the previous layer's LayerNorm parameters
           // With 225 KB of shared memory the L1 is a few KB: every parameter read would be an L2 round trip, so the layer's
           // parameters are staged in shared memory once; the first barrier of the attention phase orders them before use.
           for (int i = wt; i < 448; i += NWT) {
