@@ -10,11 +10,11 @@
 //   q4 <  3: 12 worker warps (4 per scheduler): all epilogues, both attentions; sub = column quarter of an epilogue.
 // Tensor memory (512 columns) = 4 quarters of 128 fp32 columns (Q0..Q3), handed back and forth per op with
 // ready/free mbarriers.  Shared memory:
-//   XS  [128 x 256] bf16, UMMA K-major SWIZZLE_128B (4 k-tiles)  — the residual stream AND the A operand; rows 96..127
-//                                        carry no token, so k-tile 0's rows 96..127 form the 4th weight stage
+//   XS  [128 x 256] bf16, UMMA K-major SWIZZLE_128B, stored row-group-major (xs_off)  — the residual stream AND the A
+//                                        operand; rows 96..127 carry no token: that contiguous 16 KB is the 4th weight stage
 //   BUF [128 x 256] bf16, same format — A ring of the input GEMM / rope'd h for local attention /
 //                                        attention output (A of out_proj) / FFN hidden chunk (fp16, A of linear2)
-//   W   3 x 16 KB weight stages ([128 or 64 rows] x 64 k), TMA + mbarrier ring
+//   W   3 x 16 KB weight stages ([128 or 64 rows] x 64 k) + the one inside XS, TMA + mbarrier ring
 //   Qs/Ks/Vs [96][72] bf16 per-head staging for the mma.sync attention; LayerNorm partials; barriers.
 #pragma once
 #include "dsg_tc_gemm.cuh"
