@@ -303,9 +303,11 @@ def main():
     styles_pin = styles.pin_memory()
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)     # > 126 MB L2
 
+    out_pin = torch.empty(B, n_frames - g.n_seed, g.njoints, dtype=torch.float32).pin_memory()     # the caller's result buffer
+
     def one_step(feats, out_device):
         return S.inference_batch(model, diffusion, feats, styles_pin if out_device == "cpu" else styles, seed=123456,
-                                 clip_ids=clip_ids, out_device=out_device)
+                                 clip_ids=clip_ids, out_device=out_device, out=out_pin if out_device == "cpu" else None)
 
     def timed(feats, out_device, K, W):
         for _ in range(W):
@@ -381,10 +383,10 @@ def main():
                                 "FLOPs = reference's 2*M*N*K count, excludes padding (89 -> 128 token rows) and hoisted terms"}
             # HBM traffic of the launch: x_t read and written once (fp32), its bf16 k-block image written and read once, the
             # pre-drawn noise written and read once per clip-step (everything else is on chip or L2-resident weights): ncu
-            # measured 1.99 MB per clip-step (profiles/r01_clip_kernel_v4_ncu_full_summary.csv: dram read + write of a
-            # 148-clip x 12-step launch = 3.529 GB)
-            roofline["traffic"] = 1.987e6 * B * diffusion.num_timesteps
-            roofline["traffic_note"] = "bytes per launch = ncu dram__bytes_read+write per clip-step (1.99 MB, r01 v4 capture) x clips x steps"
+            # measured 1.99 MB per clip-step (profiles/r01_clip_kernel_v5_ncu_full_summary.csv: dram read + write of a
+            # 148-clip x 12-step launch = 3.526 GB)
+            roofline["traffic"] = 1.985e6 * B * diffusion.num_timesteps
+            roofline["traffic_note"] = "bytes per launch = ncu dram__bytes_read+write per clip-step (1.99 MB, r01 v5 capture) x clips x steps"
             log("clip-kernel segment: %.1f ms (%.1f us per DDPM step), %.1f TFLOP/s" % (ms, ms * 1e3 / diffusion.num_timesteps, ach))
             try:      # where the persistent kernel spends its cycles (instrumented build of the same kernel, 50 steps)
                 os.environ["DSG_CLIP_PROF"] = "1"

@@ -101,12 +101,13 @@ def segment_plan(n_frames, n_poses, n_seed):
 
 @torch.no_grad()
 def inference_batch(model, diffusion, features, styles, *, seed=123456, clip_ids=None, smoothing=True,
-                    skip_timesteps=0, sampler='ddpm', device=None, out_device='cpu'):
+                    skip_timesteps=0, sampler='ddpm', device=None, out_device='cpu', out=None):
     """B clips x S segments through the engine.
 
-    features: sequence (len = segments) of [B, audio_frames, audio_dim] tensors (host or device) — or a callable
-    ``features(segment_index) -> tensor``;  styles: [B, style_in].
-    Returns the normalised motion [B, n_frames - n_seed, J] float32 (sample.py:291-296) on ``out_device``.
+    features: sequence (len = segments) of [B, audio_frames, audio_dim] tensors (host or device);  styles: [B, style_in].
+    Returns the normalised motion [B, n_frames - n_seed, J] float32 (sample.py:291-296) on ``out_device`` — or in ``out``
+    (e.g. a pinned host tensor of that shape: one asynchronous copy instead of a pageable one).
+    Host feature tensors in pinned memory are copied one segment ahead on a side stream, under the previous segment's loop.
     """
     g = model.geometry
     nseg = len(features) if not callable(features) else None
@@ -120,12 +121,28 @@ def inference_batch(model, diffusion, features, styles, *, seed=123456, clip_ids
     shape_ = (B, g.njoints, 1, g.n_poses)
     seed_pose = torch.zeros(B, g.njoints, 1, g.n_seed, device=dev)              # sample.py:244
     pieces, prev = [], None
+    main = torch.cuda.current_stream(dev)
+    side = torch.cuda.Stream(dev) if any((not f.is_cuda) and f.is_pinned() for f in features) else None
+
+    def fetch(i):                                                               # host (pinned) -> device, asynchronously
+        f = features[i]
+        if side is None or f.is_cuda or not f.is_pinned():
+            return f
+        with torch.cuda.stream(side):                                           # not ordered after `main`: it must overlap
+            return f.to(dev, non_blocking=True)
+
+    cur = fetch(0)
     for i in range(nseg):
-        y = {'style': styles, 'seed': seed_pose, 'audio': features[i],
+        if side is not None:
+            main.wait_stream(side)
+        y = {'style': styles, 'seed': seed_pose, 'audio': cur,
              'mask_local': torch.ones(1, g.n_poses, dtype=torch.bool),
              'noise_seed': seed, 'segment': i, 'clip_ids': clip_ids}
         sample = sample_fn(model, shape_, clip_denoised=False, model_kwargs={'y': y}, skip_timesteps=skip_timesteps,
                            init_image=None, progress=False, dump_steps=None, noise=None, const_noise=False)
+        if isinstance(cur, torch.Tensor) and cur.is_cuda:
+            cur.record_stream(main)
+        cur = fetch(i + 1) if i + 1 < nseg else None                            # overlaps with segment i's loop
         if prev is not None and g.n_seed != 0:                                    # sample.py:266-288
             tail = prev[..., -g.n_seed:].contiguous()
             pieces.append(prev[..., :-g.n_seed])
@@ -137,6 +154,13 @@ def inference_batch(model, diffusion, features, styles, *, seed=123456, clip_ids
     pieces.append(prev[..., :-g.n_seed] if g.n_seed != 0 else prev)               # sample.py:292
     seq = torch.cat(pieces, dim=-1)[:, :, 0, :].transpose(1, 2)                   # [B, n_frames, J]
     seq = seq[:, g.n_seed:] if g.n_seed != 0 else seq                             # sample.py:296
+    if out is not None:
+        if tuple(out.shape) != tuple(seq.shape) or out.dtype != torch.float32:
+            raise ValueError(f"out must be float32 {tuple(seq.shape)}")
+        out.copy_(seq, non_blocking=True)
+        if not out.is_cuda:
+            main.synchronize()
+        return out
     return seq.contiguous().to(out_device)
 
 
