@@ -176,3 +176,19 @@ def test_clip_kernel_many_clips_per_cta(sd):
     part = d.p_sample_loop(m, (3, G.njoints, 1, G.n_poses), clip_denoised=False,
                            model_kwargs={'y': dict(ys, noise_seed=SEED, segment=0, clip_ids=[147, 148, 149])})
     assert _err(part, full[147:150])[0] < 1e-5
+
+
+def test_clip_kernel_is_bitwise_reproducible(sd):
+    """Race detector: the persistent kernel synchronises 16 warps through ~40 mbarriers, named barriers and proxy fences
+    with no host involvement; any missing edge shows up as run-to-run differences.  Same inputs -> identical bits, for
+    one clip per CTA, several clips per CTA, and a single clip (different relative timing of the roles)."""
+    d = create_gaussian_diffusion([40])
+    for B in (148, 150, 1):
+        y = synthetic_conditioning(G, B, segment=1)
+        m = _model(sd, max_batch=B)
+        outs = []
+        for _ in range(3):
+            outs.append(d.p_sample_loop(m, (B, G.njoints, 1, G.n_poses), clip_denoised=False,
+                                        model_kwargs={'y': dict(y, noise_seed=SEED, segment=1, clip_ids=list(range(B)))}).clone())
+        assert bool(torch.isfinite(outs[0]).all())
+        assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2]), f"B={B}: results differ between identical runs"
