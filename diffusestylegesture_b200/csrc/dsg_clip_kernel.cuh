@@ -6,7 +6,7 @@
 //
 // Warp roles (512 threads, warp = 4 * sub + q4; q4 = TMEM lane quarter = scheduler):
 //   q4 == 3 (rows 96..127 carry no token): 3 = TMA producer (weights, x_t k-blocks, x_t / z chunks)   7 = tcgen05.mma issuer
-//                                          11, 15 = noise pre-draw (Philox)
+//                                          11 = noise pre-draw (Philox)   15 = attention issuer (S = Q K^T, O = P V)
 //   q4 <  3: 12 worker warps (4 per scheduler): all epilogues, both attentions; sub = column quarter of an epilogue.
 // Tensor memory (512 columns) = 4 quarters of 128 fp32 columns (Q0..Q3), handed back and forth per op with
 // ready/free mbarriers.  Shared memory:
@@ -36,6 +36,14 @@ constexpr int OFF_W3 = OFF_XS + 12 * 4096;      // 4th weight stage (see xs_off:
 constexpr int OFF_K = OFF_Q + 96 * QLD * 2;
 constexpr int OFF_V = OFF_K + 96 * QLD * 2;
 constexpr int OFF_RED = OFF_V + 96 * QLD * 2;
+// Global attention on tcgen05: operands in the canonical no-swizzle K-major layout [k-chunk of 8][8-row group][8 rows][16 B]
+// (descriptor: LBO = byte distance between k-chunks = groups * 128, SBO = byte distance between 8-row groups = 128).
+constexpr int AT_Q = OFF_Q;                      // A of S = Q K^T: [128 x 64]  (8 chunks x 16 groups x 128 B = 16 KB)
+constexpr int AT_K = OFF_Q + 16384;              // B of S:        [ 96 x 64]  (8 chunks x 12 groups x 128 B = 12 KB)
+constexpr int AT_P = OFF_Q;                      // A of O = P V:  [128 x 96]  (12 chunks x 16 groups = 24 KB), over Q | K once S is done
+constexpr int AT_V = OFF_Q + 28672;              // B of O = V^T:  [ 64 x 96]  (12 chunks x 8 groups = 12 KB)
+constexpr int LBO_Q = 16 * 128, LBO_K = 12 * 128, LBO_P = 16 * 128, LBO_V = 8 * 128;
+static_assert(AT_V + 12 * LBO_V <= OFF_RED, "attention operand staging must fit in the Q/K/V region");
 constexpr int OFF_B1 = OFF_RED + 2048;           // per-layer parameters (7 KB): b1[1024] fp16 | fp32 bq[256] | bo'[256] | b2[256] | 512 B | LayerNorm partials 1.5 KB;
                                                  // during the pose head its first 4.5 KB hold the head bias instead
 constexpr int OFF_LNP = OFF_BUF + 3 * KT + 12288; // rows 96..127 of BUF k-tile 3: never a token, and beyond the pose-head chunk slots (which start landing before the last LayerNorm ends): fp32 g1 | be1 | g2 | be2
@@ -58,7 +66,8 @@ constexpr int R_LAYER = 2048, R_QKV = 0, R_WO = 768, R_W1 = 1024, R_HEAD = NL * 
 
 // barrier indices
 enum { B_WFULL = 0, B_WEMPTY = 4, B_AFULL = 8, B_AEMPTY = 12, B_ACCR = 16, B_ACCF = 20, B_XSR = 24, B_BUFR = 25, B_BUFF = 27,
-       B_ZR = 29, B_ZF = 30, B_HFULL = 31, B_HEMPTY = 35, B_HGO = 39, B_XAR = 40, B_COUNT = 41 };
+       B_ZR = 29, B_ZF = 30, B_HFULL = 31, B_HEMPTY = 35, B_HGO = 39, B_XAR = 40, B_QKR = 41, B_SR = 42, B_PR = 43, B_OR = 44,
+       B_COUNT = 45 };
 
 struct ClipParams {
   float* x;                 // [B][J][T] fp32, in/out
@@ -122,6 +131,14 @@ DSG_DEVINL uint64_t make_sw128_desc_sbo(uint32_t smem_addr, uint32_t sbo) {
   d |= (uint64_t)(sbo >> 4) << 32;
   d |= (uint64_t)1 << 46;
   d |= (uint64_t)2 << 61;
+  return d;
+}
+DSG_DEVINL uint64_t make_nosw_desc(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {     // SWIZZLE_NONE, K-major
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(lbo >> 4) << 16;
+  d |= (uint64_t)(sbo >> 4) << 32;
+  d |= (uint64_t)1 << 46;
   return d;
 }
 DSG_DEVINL int wstage_off(int slot) { return slot < 3 ? OFF_W + slot * WSTAGE : OFF_W3; }
@@ -211,8 +228,9 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
     }
     mbar_init(&bars[B_XSR], NW);
     for (int i = 0; i < 2; ++i) { mbar_init(&bars[B_BUFR + i], NW); mbar_init(&bars[B_BUFF + i], 1); }
-    mbar_init(&bars[B_ZR], 2); mbar_init(&bars[B_ZF], NW);
+    mbar_init(&bars[B_ZR], 1); mbar_init(&bars[B_ZF], NW);
     mbar_init(&bars[B_HGO], 1); mbar_init(&bars[B_XAR], NW);
+    mbar_init(&bars[B_QKR], NW); mbar_init(&bars[B_SR], 1); mbar_init(&bars[B_PR], NW); mbar_init(&bars[B_OR], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_in) : "memory");
@@ -347,14 +365,17 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
             // ---- in_proj, one head at a time into alternating TMEM halves: q | k | v = 3 x 64 columns
             owait(B_XSR);
             tcgen05_fence_after();
-            for (int h = 0; h < NH; ++h) {
+            auto qkv = [&](int h) {
               const int hb = h & 1;
               owait(B_ACCF + 2 * hb); owait(B_ACCF + 2 * hb + 1);
               tcgen05_fence_after();
               for (int kb = 0; kb < 4; ++kb) tile(xs_addr + kb * 1024, hb * 256, idesc128, kb > 0, 4096);            // q | k
               for (int kb = 0; kb < 4; ++kb) tile(xs_addr + kb * 1024, hb * 256 + 128, idesc64, kb > 0, 4096);      // v
               tcgen05_commit(&bars[B_ACCR + 2 * hb]); tcgen05_commit(&bars[B_ACCR + 2 * hb + 1]);
-            }
+            };
+            // (S = Q K^T and O = P V of every head are issued by the attention issuer, warp 15; a head's TMEM half comes back
+            //  after its O epilogue, which is what in_proj(h + 2) waits for)
+            for (int h = 0; h < NH; ++h) qkv(h);
             // ---- out_proj: A = attention output in BUF, D = Q0|Q1
             owait(B_BUFR + 0); owait(B_BUFR + 1);
             owait(B_ACCF + 0); owait(B_ACCF + 1);
@@ -397,10 +418,9 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
         }
       if (prof) { P.prof[PF_TOTAL] = clock64() - t_begin; P.prof[PF_MMA_WAIT_W] = t_w; P.prof[PF_MMA_WAIT_OTHER] = t_o; }
     }
-  } else if (q4 == 3) {
+  } else if (q4 == 3 && sub == 2) {
     // =================================================== noise pre-draw ===================================================
     Phases ph{1ull << B_ZF};
-    const int nt = (sub - 2) * 32 + lane;            // 0..63
     for (int clip = blockIdx.x; clip < P.B; clip += gridDim.x) {
       const uint32_t cid = (uint32_t)P.clip_ids[clip];
       float* zc = P.z + (long long)clip * J * T;
@@ -408,12 +428,42 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
         const int index = first_index - k;
         if (index == 0 || P.sampler != 0) continue;
         ph.wait(bars, B_ZF);
-        for (int q = nt; q < J * T / 4; q += 64)
+        for (int q = lane; q < J * T / 4; q += 32)
           *reinterpret_cast<float4*>(zc + 4 * q) = philox_normal4((uint32_t)q, (uint32_t)(1 + k), cid, segment, key0, key1);
         fence_async_all();                               // z is read back through the async proxy (bulk copies)
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars[B_ZR]);
       }
+    }
+  } else if (q4 == 3) {
+    // =================================================== attention issuer ===================================================
+    // Global attention of every head on the tensor core, from its own thread so that it never queues behind a weight tile:
+    // S = Q K^T into columns [0, 96) of the head's TMEM half (the q | k accumulators are already extracted), then O = P V
+    // into columns [96, 160).  Operands: canonical no-swizzle core-matrix layouts (AT_*); V is the MN-major B operand.
+    if (lane == 0) {
+      Phases ph{0};
+      const uint32_t smem_addr0 = smem_u32(smem);
+      constexpr uint32_t idesc_s = make_idesc_bf16(128, 96), idesc_o = make_idesc_bf16(128, 64) | (1u << 16);
+      for (int clip = blockIdx.x; clip < P.B; clip += gridDim.x)
+        for (int k = 0; k < P.n_run; ++k)
+          for (int l = 0; l < NL; ++l)
+            for (int h = 0; h < NH; ++h) {
+              const uint32_t d0 = tmem + (uint32_t)((h & 1) * 256);
+              ph.wait(bars, B_QKR);
+              tcgen05_fence_after();
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                umma_bf16(d0, make_nosw_desc(smem_addr0 + AT_Q + j * 2 * LBO_Q, LBO_Q, 128),
+                          make_nosw_desc(smem_addr0 + AT_K + j * 2 * LBO_K, LBO_K, 128), idesc_s, j > 0 ? 1u : 0u);
+              tcgen05_commit(&bars[B_SR]);
+              ph.wait(bars, B_PR);
+              tcgen05_fence_after();
+#pragma unroll
+              for (int j = 0; j < 6; ++j)
+                umma_bf16(d0 + 96, make_nosw_desc(smem_addr0 + AT_P + j * 2 * LBO_P, LBO_P, 128),
+                          make_nosw_desc(smem_addr0 + AT_V + j * 2 * LBO_V, LBO_V, 128), idesc_o, j > 0 ? 1u : 0u);
+              tcgen05_commit(&bars[B_OR]);
+            }
     }
   } else {
     // =================================================== workers ===================================================
@@ -676,134 +726,98 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
             ph.wait(bars, B_ACCR + 2 * hb); ph.wait(bars, B_ACCR + 2 * hb + 1);
             lap(PF_W_QKV_WAIT);
             tcgen05_fence_after();
-            // q | k | v of this head: 12 chunks of 16 columns, three per column quarter (one wait for the three TMEM loads)
+            const uint32_t thalf = tlane + (uint32_t)(hb * 256);
+            // ---- q | k | v of this head -> tcgen05 operands.  Thread = (token row r, 16-column slice `sub` of each of q, k, v).
             {
               float v48[48];
-              tmem_ld16_issue(tlane + hb * 256 + (sub * 3) * 16, v48);
-              tmem_ld16_issue(tlane + hb * 256 + (sub * 3 + 1) * 16, v48 + 16);
-              tmem_ld16_issue(tlane + hb * 256 + (sub * 3 + 2) * 16, v48 + 32);
+              tmem_ld16_issue(thalf + sub * 16, v48);
+              tmem_ld16_issue(thalf + 64 + sub * 16, v48 + 16);
+              tmem_ld16_issue(thalf + 128 + sub * 16, v48 + 32);
               tmem_ld_wait(); tie32(v48); tie4(v48 + 32); tie4(v48 + 36); tie4(v48 + 40); tie4(v48 + 44);
+              uint8_t* qd = smem + AT_Q + (sub * 2) * LBO_Q + (r >> 3) * 128 + (r & 7) * 16;
+              uint8_t* kd = smem + AT_K + (sub * 2) * LBO_K + (r >> 3) * 128 + (r & 7) * 16;
+              uint8_t* vd = smem + AT_V + (r >> 3) * LBO_V + (sub * 2) * 128 + (r & 7) * 16;      // MN-major: [key group][d group][key][8 d]
+              if (r < S) {
+                const float* bq = b1s + 512 + h * 64 + sub * 16;
 #pragma unroll
-              for (int ci = 0; ci < 3; ++ci) {
-                const int ch = sub * 3 + ci;             // 0..11: q = 0..3, k = 4..7, v = 8..11
-                float* v16 = v48 + 16 * ci;
-                __nv_bfloat16* dst = (ch < 4 ? Qs : (ch < 8 ? Ks : Vs)) + r * QLD + (ch & 3) * 16;
-                if (r < S) {
-                  if (ch < 4) {
-                    const float* bq = b1s + 512 + h * 64 + ch * 16;
-#pragma unroll
-                    for (int i = 0; i < 16; i += 4) {
-                      const float4 b4 = *reinterpret_cast<const float4*>(bq + i);
-                      v16[i] += b4.x; v16[i + 1] += b4.y; v16[i + 2] += b4.z; v16[i + 3] += b4.w;
-                    }
-                  }
-                  *reinterpret_cast<uint4*>(dst) = pack8(v16);
-                  *reinterpret_cast<uint4*>(dst + 8) = pack8(v16 + 8);
-                } else {
-                  *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u);
-                  *reinterpret_cast<uint4*>(dst + 8) = make_uint4(0u, 0u, 0u, 0u);
+                for (int i = 0; i < 16; i += 4) {
+                  const float4 b4 = *reinterpret_cast<const float4*>(bq + i);
+                  v48[i] += b4.x; v48[i + 1] += b4.y; v48[i + 2] += b4.z; v48[i + 3] += b4.w;
                 }
+                *reinterpret_cast<uint4*>(qd) = pack8(v48);          *reinterpret_cast<uint4*>(qd + LBO_Q) = pack8(v48 + 8);
+                *reinterpret_cast<uint4*>(kd) = pack8(v48 + 16);     *reinterpret_cast<uint4*>(kd + LBO_K) = pack8(v48 + 24);
+                *reinterpret_cast<uint4*>(vd) = pack8(v48 + 32);     *reinterpret_cast<uint4*>(vd + 128) = pack8(v48 + 40);
+              } else {
+                const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
+                *reinterpret_cast<uint4*>(qd) = z4; *reinterpret_cast<uint4*>(qd + LBO_Q) = z4;
+                *reinterpret_cast<uint4*>(kd) = z4; *reinterpret_cast<uint4*>(kd + LBO_K) = z4;
+                *reinterpret_cast<uint4*>(vd) = z4; *reinterpret_cast<uint4*>(vd + 128) = z4;
               }
             }
-            release_acc(2 * hb, 2 * hb + 1, false, -1);
             if (l > 0 && hb == 0) ph.wait(bars, B_BUFF + (h >> 1));    // linear2 of the previous layer has consumed this BUF half
+            tcgen05_fence_before();
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars[B_QKR]);
             lap(PF_W_EXTRACT);
-            workers_sync();
+            // ---- softmax over the 96 key columns of S (thread = row r, keys 24 sub .. 24 sub + 23); P (bf16) -> A operand of P V
+            ph.wait(bars, B_SR);
             lap(PF_W_SYNC1);
+            tcgen05_fence_after();
             {
-              // ---- softmax(q k^T / 8) v: warp = (16 query rows, one half of the keys); the two partial results of a row block
-              // are merged flash-style through 36 spare TMEM columns of the pair's lane quarter
-              const int rb = q4 * 2 + (sub & 1), kh = sub >> 1;
-              const int r0 = rb * 16, key0 = kh * 48;
-              float sc[6][4];
+              float sc[24];
+              tmem_ld16_issue(thalf + sub * 24, sc);
+              tmem_ld8_issue(thalf + sub * 24 + 16, sc + 16);
+              tmem_ld_wait();
 #pragma unroll
-              for (int nt = 0; nt < 6; ++nt) { sc[nt][0] = sc[nt][1] = sc[nt][2] = sc[nt][3] = 0.f; }
+              for (int i = 0; i < 24; i += 4) tie4(sc + i);
+              float mx = -3.0e38f;
 #pragma unroll
-              for (int kk = 0; kk < 4; ++kk) {
-                uint32_t a[4];
-                ldsm_x4(a[0], a[1], a[2], a[3], Qs + (r0 + (lane & 7) + ((lane >> 3) & 1) * 8) * QLD + kk * 16 + (lane >> 4) * 8);
-#pragma unroll
-                for (int np = 0; np < 3; ++np) {
-                  uint32_t b0, b1, b2, b3;
-                  ldsm_x4(b0, b1, b2, b3, Ks + (key0 + np * 16 + (lane & 7) + (lane >> 4) * 8) * QLD + kk * 16 + ((lane >> 3) & 1) * 8);
-                  mma_bf16_16816(sc[2 * np], a, b0, b1);
-                  mma_bf16_16816(sc[2 * np + 1], a, b2, b3);
-                }
+              for (int i = 0; i < 24; ++i) {
+                if (sub * 24 + i >= S) sc[i] = -3.0e38f;
+                mx = fmaxf(mx, sc[i]);
               }
-              const int cbase = (lane & 3) * 2;
-              float mx0 = -3.0e38f, mx1 = -3.0e38f;
-#pragma unroll
-              for (int nt = 0; nt < 6; ++nt) {
-                const int c = key0 + nt * 8 + cbase;
-                if (c >= S) { sc[nt][0] = -3.0e38f; sc[nt][2] = -3.0e38f; }
-                if (c + 1 >= S) { sc[nt][1] = -3.0e38f; sc[nt][3] = -3.0e38f; }
-                mx0 = fmaxf(mx0, fmaxf(sc[nt][0], sc[nt][1]));
-                mx1 = fmaxf(mx1, fmaxf(sc[nt][2], sc[nt][3]));
-              }
-              mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
-              mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+              red_s[sub * 96 + r] = mx;
+              workers_sync();
+              mx = fmaxf(fmaxf(red_s[r], red_s[96 + r]), fmaxf(red_s[192 + r], red_s[288 + r]));
               const float sl2 = 1.4426950408889634f * 0.125f;
-              float s0 = 0.f, s1 = 0.f;
+              float sum = 0.f;
 #pragma unroll
-              for (int nt = 0; nt < 6; ++nt) {
-                sc[nt][0] = exp2f((sc[nt][0] - mx0) * sl2); sc[nt][1] = exp2f((sc[nt][1] - mx0) * sl2);
-                sc[nt][2] = exp2f((sc[nt][2] - mx1) * sl2); sc[nt][3] = exp2f((sc[nt][3] - mx1) * sl2);
-                s0 += sc[nt][0] + sc[nt][1]; s1 += sc[nt][2] + sc[nt][3];
-              }
-              s0 += __shfl_xor_sync(0xffffffffu, s0, 1); s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
-              s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
-              float oc[36];                              // [8 d-tiles][4] + (mx0, mx1, s0, s1)
+              for (int i = 0; i < 24; ++i) { sc[i] = exp2f((sc[i] - mx) * sl2); sum += sc[i]; }
+              red_q[sub * 96 + r] = sum;
+              uint8_t* pd = smem + AT_P + (sub * 3) * LBO_P + (r >> 3) * 128 + (r & 7) * 16;
+              *reinterpret_cast<uint4*>(pd) = pack8(sc);
+              *reinterpret_cast<uint4*>(pd + LBO_P) = pack8(sc + 8);
+              *reinterpret_cast<uint4*>(pd + 2 * LBO_P) = pack8(sc + 16);
+            }
+            tcgen05_fence_before();
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars[B_PR]);
+            lap(PF_W_ATT_MMA);
+            // ---- O / sum -> BUF (A operand of out_proj), 16 head-dim columns per thread
+            ph.wait(bars, B_OR);
+            tcgen05_fence_after();
+            {
+              float o16[16];
+              tmem_ld16_issue(thalf + 96 + sub * 16, o16);
+              tmem_ld_wait();
 #pragma unroll
-              for (int i = 0; i < 32; ++i) oc[i] = 0.f;
+              for (int i = 0; i < 16; i += 4) tie4(o16 + i);
+              const float inv = 1.0f / (red_q[r] + red_q[96 + r] + red_q[192 + r] + red_q[288 + r]);
 #pragma unroll
-              for (int kt = 0; kt < 3; ++kt) {
-                uint32_t a[4];
-                a[0] = pack_bf16x2(sc[2 * kt][0], sc[2 * kt][1]); a[1] = pack_bf16x2(sc[2 * kt][2], sc[2 * kt][3]);
-                a[2] = pack_bf16x2(sc[2 * kt + 1][0], sc[2 * kt + 1][1]); a[3] = pack_bf16x2(sc[2 * kt + 1][2], sc[2 * kt + 1][3]);
-#pragma unroll
-                for (int dp = 0; dp < 4; ++dp) {
-                  uint32_t b0, b1, b2, b3;
-                  ldsm_x4_t(b0, b1, b2, b3, Vs + (key0 + kt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * QLD + dp * 16 + (lane >> 4) * 8);
-                  mma_bf16_16816(*reinterpret_cast<float(*)[4]>(oc + 8 * dp), a, b0, b1);
-                  mma_bf16_16816(*reinterpret_cast<float(*)[4]>(oc + 8 * dp + 4), a, b2, b3);
-                }
-              }
-              lap(PF_W_ATT_MMA);
-              const uint32_t scratch = tlane + (uint32_t)((sub & 1) * 256 + 192);
-              if (kh == 1) {
-                oc[32] = mx0; oc[33] = mx1; oc[34] = s0; oc[35] = s1;
-                tmem_st32(scratch, oc);
-                tmem_st4(scratch + 32, oc + 32);
-                tcgen05_fence_before();
-              }
-              pair_sync(2 + rb);
-              if (kh == 0) {
-                float ob[36];
-                tcgen05_fence_after();
-                tmem_ld32_issue(scratch, ob); tmem_ld4_issue(scratch + 32, ob + 32);
-                tmem_ld_wait(); tie32(ob); tie4(ob + 32);
-                // (m, s, O) of the two key halves -> one softmax: scale each side by 2^((m_side - m) / 8 * log2 e)
-                const float m0 = fmaxf(mx0, ob[32]), m1 = fmaxf(mx1, ob[33]);
-                const float fa0 = exp2f((mx0 - m0) * sl2), fb0 = exp2f((ob[32] - m0) * sl2);
-                const float fa1 = exp2f((mx1 - m1) * sl2), fb1 = exp2f((ob[33] - m1) * sl2);
-                const float i0 = 1.0f / (s0 * fa0 + ob[34] * fb0), i1 = 1.0f / (s1 * fa1 + ob[35] * fb1);
-                const float a0 = fa0 * i0, b0 = fb0 * i0, a1 = fa1 * i1, b1 = fb1 * i1;
-                const int row0 = r0 + (lane >> 2), row1 = row0 + 8;
-#pragma unroll
-                for (int dt = 0; dt < 8; ++dt) {
-                  const int c = h * HD + dt * 8 + cbase;
-                  *reinterpret_cast<uint32_t*>(BUF + a_off(row0, c)) =
-                      pack_bf16x2(oc[4 * dt] * a0 + ob[4 * dt] * b0, oc[4 * dt + 1] * a0 + ob[4 * dt + 1] * b0);
-                  *reinterpret_cast<uint32_t*>(BUF + a_off(row1, c)) =
-                      pack_bf16x2(oc[4 * dt + 2] * a1 + ob[4 * dt + 2] * b1, oc[4 * dt + 3] * a1 + ob[4 * dt + 3] * b1);
-                }
-              }
+              for (int i = 0; i < 16; ++i) o16[i] *= inv;
+              *reinterpret_cast<uint4*>(BUF + a_off(r, h * HD + sub * 16)) = pack8(o16);
+              *reinterpret_cast<uint4*>(BUF + a_off(r, h * HD + sub * 16 + 8)) = pack8(o16 + 8);
+            }
+            tcgen05_fence_before();
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              mbar_arrive(&bars[B_ACCF + 2 * hb]); mbar_arrive(&bars[B_ACCF + 2 * hb + 1]);      // the head's TMEM half is free
+              if (hb == 1) mbar_arrive(&bars[B_BUFR + (h >> 1)]);                                  // both heads of this BUF half are written
             }
             lap(PF_W_ATT_MERGE);
-            fence_async_smem();
-            workers_sync();                              // staging may be overwritten; this head's k-tile of BUF is complete
-            if (hb == 1 && lane == 0) mbar_arrive(&bars[B_BUFR + (h >> 1)]);
-            lap(PF_W_ATT);
           }
           layernorm_epilogue(b1s + 768, lnp, lnp + 256);
           // ---- FFN: GELU epilogue per 128-unit chunk -> BUF half (c & 1) as the (fp16) A operand of linear2
