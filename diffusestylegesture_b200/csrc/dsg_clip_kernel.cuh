@@ -7,7 +7,7 @@
 // Warp roles (512 threads, warp = 4 * sub + q4; q4 = TMEM lane quarter = scheduler):
 //   q4 == 3 (rows 96..127 carry no token): 3 = TMA producer (weights, x_t k-blocks, x_t / z chunks)   7 = tcgen05.mma issuer
 //                                          11 = noise pre-draw (Philox)   15 = attention issuer (S = Q K^T, O = P V)
-//   q4 <  3: 12 worker warps (4 per scheduler): all epilogues, both attentions; sub = column quarter of an epilogue.
+//   q4 <  3: 12 worker warps (4 per scheduler): all epilogues, softmax, local attention; sub = column quarter of an epilogue.
 // Tensor memory (512 columns) = 4 quarters of 128 fp32 columns (Q0..Q3), handed back and forth per op with
 // ready/free mbarriers.  Shared memory:
 //   XS  [128 x 256] bf16, UMMA K-major SWIZZLE_128B, stored row-group-major (xs_off)  — the residual stream AND the A
@@ -15,7 +15,7 @@
 //   BUF [128 x 256] bf16, same format — A ring of the input GEMM / rope'd h for local attention /
 //                                        attention output (A of out_proj) / FFN hidden chunk (fp16, A of linear2)
 //   W   3 x 16 KB weight stages ([128 or 64 rows] x 64 k) + the one inside XS, TMA + mbarrier ring
-//   Qs/Ks/Vs [96][72] bf16 per-head staging for the mma.sync attention; LayerNorm partials; barriers.
+//   AT_Q/K/P/V: per-head operands of the tcgen05 attention (no-swizzle core-matrix layouts, 40 KB); LayerNorm partials; barriers.
 #pragma once
 #include "dsg_tc_gemm.cuh"
 #include "dsg_tc_kernels.cuh"
