@@ -383,10 +383,10 @@ def main():
                                 "FLOPs = reference's 2*M*N*K count, excludes padding (89 -> 128 token rows) and hoisted terms"}
             # HBM traffic of the launch: x_t read and written once (fp32), its bf16 k-block image written and read once, the
             # pre-drawn noise written and read once per clip-step (everything else is on chip or L2-resident weights): ncu
-            # measured 1.99 MB per clip-step (profiles/r01_clip_kernel_v5_ncu_full_summary.csv: dram read + write of a
-            # 148-clip x 12-step launch = 3.526 GB)
-            roofline["traffic"] = 1.985e6 * B * diffusion.num_timesteps
-            roofline["traffic_note"] = "bytes per launch = ncu dram__bytes_read+write per clip-step (1.99 MB, r01 v5 capture) x clips x steps"
+            # measured 1.95 MB per clip-step (profiles/r01_clip_kernel_v6_ncu_full_summary.csv: dram read + write of a
+            # 148-clip x 12-step launch = 3.458 GB)
+            roofline["traffic"] = 1.947e6 * B * diffusion.num_timesteps
+            roofline["traffic_note"] = "bytes per launch = ncu dram__bytes_read+write per clip-step (1.95 MB, r01 v6 capture) x clips x steps"
             log("clip-kernel segment: %.1f ms (%.1f us per DDPM step), %.1f TFLOP/s" % (ms, ms * 1e3 / diffusion.num_timesteps, ach))
             try:      # where the persistent kernel spends its cycles (instrumented build of the same kernel, 50 steps)
                 os.environ["DSG_CLIP_PROF"] = "1"
