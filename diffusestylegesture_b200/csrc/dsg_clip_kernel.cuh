@@ -30,12 +30,10 @@ constexpr int KT = 16384;                   // one A k-tile [128 x 64] bf16
 constexpr int OFF_XS = 0;
 constexpr int OFF_BUF = 4 * KT;
 constexpr int OFF_W = 8 * KT;
-constexpr int QLD = 72;                     // Qs/Ks/Vs row stride (bf16 elements): 16 B pad -> conflict-free ldmatrix
+constexpr int AT_BYTES = 41472;             // attention operand staging (Q | K -> P, V); doubles as pose-head chunk slots
 constexpr int OFF_Q = OFF_W + 3 * WSTAGE;
 constexpr int OFF_W3 = OFF_XS + 12 * 4096;      // 4th weight stage (see xs_off: XS is stored row-group-major)
-constexpr int OFF_K = OFF_Q + 96 * QLD * 2;
-constexpr int OFF_V = OFF_K + 96 * QLD * 2;
-constexpr int OFF_RED = OFF_V + 96 * QLD * 2;
+constexpr int OFF_RED = OFF_Q + AT_BYTES;
 // Global attention on tcgen05: operands in the canonical no-swizzle K-major layout [k-chunk of 8][8-row group][8 rows][16 B]
 // (descriptor: LBO = byte distance between k-chunks = groups * 128, SBO = byte distance between 8-row groups = 128).
 constexpr int AT_Q = OFF_Q;                      // A of S = Q K^T: [128 x 64]  (8 chunks x 16 groups x 128 B = 16 KB)
@@ -57,7 +55,7 @@ constexpr int ZLD = 264;                    // rope'd h staging row stride (bf16
 constexpr int ZROWS = 104;
 static_assert(ZROWS * ZLD * 2 <= 4 * KT, "Z staging must fit in BUF");
 static_assert(SMEM_BYTES <= 232448, "shared memory budget");
-static_assert(5 * HBYTES <= 4 * KT && 3 * HBYTES <= 3 * 96 * QLD * 2, "pose-head slots");
+static_assert(5 * HBYTES <= 4 * KT && 3 * HBYTES <= AT_BYTES, "pose-head slots");
 
 // per-layer fp32 parameter block (biases, LayerNorm): offsets in floats
 constexpr int P_BQKV = 0, P_BO = 768, P_G1 = 1024, P_BE1 = 1280, P_B1 = 1536, P_B2 = 2560, P_G2 = 2816, P_BE2 = 3072, P_SIZE = 3328;
@@ -95,20 +93,10 @@ DSG_DEVINL void mbar_arrive(uint64_t* bar) {
 DSG_DEVINL void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 constexpr int NW = 12, NWT = NW * 32;          // worker warps / threads
 DSG_DEVINL void workers_sync() { asm volatile("bar.sync 1, 384;" ::: "memory"); }
-DSG_DEVINL void pair_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
 DSG_DEVINL void tmem_ld8_issue(uint32_t taddr, float* v) {
   uint32_t* r = reinterpret_cast<uint32_t*>(v);
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr));
-}
-DSG_DEVINL void tmem_ld4_issue(uint32_t taddr, float* v) {
-  uint32_t* r = reinterpret_cast<uint32_t*>(v);
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];\n" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr));
-}
-DSG_DEVINL void tmem_st4(uint32_t taddr, const float* v) {
-  const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]) : "memory");
-  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 DSG_DEVINL void tie4(float* v) { asm volatile("" : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]) :: "memory"); }
 DSG_DEVINL void ldsm_x2(uint32_t& r0, uint32_t& r1, const void* p) {
@@ -475,9 +463,6 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
     const uint32_t tlane = tmem + ((uint32_t)(q4 * 32) << 16);
     Phases ph{(0x3ull << B_BUFF)};
     __nv_bfloat16* Zs = reinterpret_cast<__nv_bfloat16*>(smem + OFF_BUF);
-    __nv_bfloat16* Qs = reinterpret_cast<__nv_bfloat16*>(smem + OFF_Q);
-    __nv_bfloat16* Ks = reinterpret_cast<__nv_bfloat16*>(smem + OFF_K);
-    __nv_bfloat16* Vs = reinterpret_cast<__nv_bfloat16*>(smem + OFF_V);
     float* red_s = reinterpret_cast<float*>(smem + OFF_RED);            // [4][96] row sums
     float* red_q = reinterpret_cast<float*>(smem + OFF_B1 + 5632);      // [4][96] row sums of squares
     float* b1s = reinterpret_cast<float*>(smem + OFF_B1);
