@@ -227,3 +227,22 @@ def test_bvh_writer_is_vectorised_and_stable(tmp_path):
     row = lines[k + 3].split(" ")
     assert len(row) == 3 + 75 * 3 + 1 and row[-1] == ""                           # "%f " per value, trailing space
     assert abs(float(row[0]) - pos[0, 0, 0]) < 1e-6
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU arm the driver runs next to ours): one JSON line on stdout with the contract keys,
+    the same metric / unit / direction as our arm, a cpu_baseline describing the run, zero copy bytes."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
+                          "--ref-sample-steps", "2", "--ref-batch", "2"], capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, out.stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "frames/s" and d["higher_is_better"] is True and d["n_gpus"] == 1
+    assert d["metric"].startswith("motion frames/sec") and d["value"] > 0 and d["steps"] == 1 and d["warmup"] == 1
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
