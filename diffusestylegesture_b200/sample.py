@@ -46,8 +46,15 @@ DEFAULT_STATS = os.path.join(_HERE, 'configs', 'zeggs_mean_std.npz')
 
 
 class Config(dict):
-    """Attribute-style dict (stands in for easydict.EasyDict, sample.py:414)."""
-    __getattr__ = dict.__getitem__
+    """Attribute-style dict (stands in for easydict.EasyDict, sample.py:414).  Missing attributes raise
+    ``AttributeError`` (as easydict does), so ``getattr(cfg, k, default)`` / ``hasattr`` / ``copy`` / ``pickle`` work."""
+
+    def __getattr__(self, name):
+        try:
+            return self[name]
+        except KeyError:
+            raise AttributeError(name) from None
+
     __setattr__ = dict.__setitem__
 
 
@@ -56,17 +63,16 @@ def create_model_and_diffusion(args):
     model = MDM(modeltype='', njoints=1141, nfeats=1, translation=True, pose_rep='rot6d', glob=True, glob_rot=True,
                 cond_mode='cross_local_attention3_style1', clip_version='ViT-B/32', action_emb='tensor',
                 audio_feat=args.audio_feat, arch='trans_enc', latent_dim=256, n_seed=8,
-                n_poses=getattr(args, 'n_poses', 88) if not isinstance(args, dict) else args.get('n_poses', 88),
-                precision=_get(args, 'precision', 'bf16'), max_batch=_get(args, 'max_batch', 1))
+                n_poses=_get(args, 'n_poses', 88),
+                precision=_get(args, 'precision', 'bf16'), max_batch=max(1, int(_get(args, 'max_batch', 1) or 1)))
     diffusion = create_gaussian_diffusion(_get(args, 'timestep_respacing', ''))
     return model, diffusion
 
 
 def _get(args, key, default):
-    try:
-        return args[key] if isinstance(args, dict) else getattr(args, key)
-    except (KeyError, AttributeError):
-        return default
+    if isinstance(args, dict):
+        return args.get(key, default)
+    return getattr(args, key, default)
 
 
 def wavlm_init(device=None, wavlm_model_path='./WavLM/WavLM-Large.pt', max_batch=16):
@@ -116,7 +122,11 @@ def inference_batch(model, diffusion, features, styles, *, seed=123456, clip_ids
     B = styles.shape[0]
     eng = model.get_engine(B)
     dev = eng.device
-    sample_fn = diffusion.p_sample_loop if sampler == 'ddpm' else diffusion.ddim_sample_loop
+    if callable(diffusion) and not hasattr(diffusion, 'p_sample_loop'):
+        sample_fn = diffusion                    # any callable with the p_sample_loop signature (sample.py:253)
+    else:
+        sample_fn = {'ddpm': 'p_sample_loop', 'ddim': 'ddim_sample_loop', 'plms': 'plms_sample_loop'}[sampler]
+        sample_fn = getattr(diffusion, sample_fn)
     styles = torch.as_tensor(styles, dtype=torch.float32)
     shape_ = (B, g.njoints, 1, g.n_poses)
     seed_pose = torch.zeros(B, g.njoints, 1, g.n_seed, device=dev)              # sample.py:244
@@ -182,8 +192,10 @@ def inference(args, wavlm_model, audio, sample_fn, model, n_frames=0, smoothing=
     g = model.geometry
     n_poses = _get(args, 'n_poses', g.n_poses)
     if features is None:
-        if n_frames == 0:
-            n_frames = audio.shape[0] * 20 // 16000
+        avail = audio.shape[0] * 20 // 16000
+        n_frames = avail if n_frames == 0 else min(n_frames, avail)
+        if n_frames < n_poses - n_seed:
+            raise ValueError(f"{n_frames} frames of audio: shorter than one segment stride ({n_poses - n_seed} frames)")
         nseg, n_frames = segment_plan(n_frames, n_poses, n_seed)
         audio = audio[:int(n_frames * 16000 / 20)]
         stride = n_poses - n_seed
@@ -198,12 +210,10 @@ def inference(args, wavlm_model, audio, sample_fn, model, n_frames=0, smoothing=
     else:
         nseg = len(features)
         n_frames = nseg * (n_poses - n_seed)
-    diffusion = getattr(sample_fn, '__self__', None)
-    if diffusion is None:
-        raise ValueError("sample_fn must be diffusion.p_sample_loop or diffusion.ddim_sample_loop")
-    sampler = 'ddim' if sample_fn.__name__ == 'ddim_sample_loop' else 'ddpm'
-    seq = inference_batch(model, diffusion, features, torch.as_tensor([style], dtype=torch.float32), seed=seed,
-                          smoothing=smoothing, skip_timesteps=skip_timesteps, sampler=sampler)
+    # the reference calls sample_fn(model, shape, ...) as a plain callable (sample.py:253): bound sampler methods of the
+    # diffusion object, functools.partial of them and user wrappers all work
+    seq = inference_batch(model, sample_fn, features, torch.as_tensor([style], dtype=torch.float32), seed=seed,
+                          smoothing=smoothing, skip_timesteps=skip_timesteps)
     out_poses = denormalise(seq[0].numpy(), stats_path)
     print(out_poses.shape)
     prefix = str(datetime.now().strftime('%Y%m%d_%H%M%S'))
@@ -249,7 +259,7 @@ def main(args, save_dir, model_path, audio_path=None, mfcc_path=None, audiowavlm
     model.to(torch.device('cuda:' + str(args.gpu)))
     model.eval()
     sample_fn = diffusion.p_sample_loop if _get(args, 'sampler', 'ddpm') == 'ddpm' else diffusion.ddim_sample_loop
-    style = style2onehot[audiowavlm_path.split('/')[-1].split('_')[1]]
+    style = style2onehot[style_from_filename(audiowavlm_path)]
     print(style)
     audio = None
     if features is None:
@@ -259,6 +269,21 @@ def main(args, save_dir, model_path, audio_path=None, mfcc_path=None, audiowavlm
         audio, _ = load_wav_16k(audiowavlm_path)
     return inference(args, wavlm_model, audio, sample_fn, model, n_frames=max_len, smoothing=True, SG_filter=True,
                      minibatch=True, skip_timesteps=0, style=style, seed=123456, features=features, save_dir=save_dir)
+
+
+def style_from_filename(path):
+    """sample.py:378: the style is token 1 of the '_'-separated file name (e.g. 015_Happy_4_x_1_0.wav)."""
+    parts = os.path.basename(path).split('_')
+    if len(parts) < 2:
+        raise ValueError(f"{path}: no style given and the file name has no '_<Style>_' token (sample.py:378)")
+    return parts[1]
+
+
+def auto_max_batch(n_clips, device):
+    """Clips per engine launch when the config does not pin it: the clip kernel runs one persistent CTA (pair) per clip,
+    so up to two waves of the SM count keep every SM busy; fewer clips than that run as one batch."""
+    sms = torch.cuda.get_device_properties(device).multi_processor_count if torch.cuda.is_available() else 148
+    return max(1, min(int(n_clips), 2 * sms))
 
 
 def read_manifest(path):
@@ -273,7 +298,7 @@ def read_manifest(path):
             if not rec or not rec[0] or rec[0].startswith('#') or rec[0].lower() in ('wav', 'wav_path', 'path'):
                 continue
             wav = rec[0]
-            tok = rec[1] if len(rec) > 1 and rec[1] else os.path.basename(wav).split('_')[1]
+            tok = rec[1] if len(rec) > 1 and rec[1] else style_from_filename(wav)
             if tok in style2onehot:
                 style = style2onehot[tok]
             elif tok.isdigit() and int(tok) < 6:
@@ -318,7 +343,7 @@ def main_batch(args, save_dir, model_path, manifest, max_len=0, wavlm_model=None
     rows = read_manifest(manifest) if isinstance(manifest, str) else manifest
     os.makedirs(save_dir, exist_ok=True)
     dev = torch.device('cuda:' + str(_get(args, 'gpu', '0')))
-    max_batch = int(_get(args, 'max_batch', 148))
+    max_batch = int(_get(args, 'max_batch', 0) or 0) or auto_max_batch(len(rows), dev)
     if model is None:
         cfg = dict(args) if isinstance(args, dict) else dict(vars(args))
         cfg['max_batch'] = max_batch
@@ -330,10 +355,14 @@ def main_batch(args, save_dir, model_path, manifest, max_len=0, wavlm_model=None
     g = model.geometry
     sampler = _get(args, 'sampler', 'ddpm')
     wins = []
+    stride = g.n_poses - g.n_seed
     for r in rows:
         audio = r['audio'] if 'audio' in r else load_wav_16k(r['wav'])[0]
         n_frames = max_len if max_len else audio.shape[0] * 20 // 16000
         n_frames = min(n_frames, audio.shape[0] * 20 // 16000)
+        if n_frames < stride:          # the reference would run one ragged segment and fail inside the local attention
+            raise ValueError(f"{r['wav']}: {n_frames} frames of audio, shorter than one segment stride ({stride} frames = "
+                             f"{stride / 20:.1f} s); pad the clip or drop it from the manifest")
         wins.append(segment_windows(audio, n_frames, g.n_poses, g.n_seed))
     paths = [None] * len(rows)
 
@@ -362,17 +391,21 @@ def parse_cli(argv=None):
     parser = argparse.ArgumentParser(description='DiffuseStyleGesture')
     parser.add_argument('--config', default=DEFAULT_CONFIG)
     parser.add_argument('--gpu', type=str, default='0')
-    parser.add_argument('--no_cuda', type=list, default=['0'])
+    parser.add_argument('--no_cuda', type=list, default=['0'])     # parsed and never read, exactly as in the reference (sample.py:403)
     parser.add_argument('--model_path', type=str, default='./model000450000.pt')
     parser.add_argument('--audiowavlm_path', type=str, default='')
     parser.add_argument('--max_len', type=int, default=0)
     parser.add_argument('--batch', type=str, default='', help='CSV manifest (wav,style[,clip_id]) -> one BVH per row (additive)')
     parser.add_argument('--save_dir', type=str, default='sample_dir')
     parser.add_argument('--wavlm_path', type=str, default='./WavLM/WavLM-Large.pt')
+    parser.add_argument('--max_batch', type=int, default=None,
+                        help='clips per engine launch for --batch (default: config value; 0 = auto)')
     args = parser.parse_args(argv)
     with open(args.config) as f:
         config = yaml.safe_load(f)
     for k, v in vars(args).items():
+        if k == 'max_batch' and v is None:       # flag not given: keep the YAML value
+            continue
         config[k] = v
     return Config(config)
 
