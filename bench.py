@@ -109,30 +109,58 @@ T0 = time.perf_counter()
 
 
 def cpu_baseline(sample_steps, batch, threads):
-    """Oracle port of the reference sampler on the host cores: `sample_steps` DDPM steps of one segment at batch
-    `batch`, extrapolated linearly to 4 segments x 1000 steps (every step costs the same: same shapes)."""
+    """The reference sampler on the host cores: `sample_steps` DDPM steps of one 88-frame segment at batch `batch`,
+    extrapolated linearly to 4 segments x 1000 steps (every step costs the same: same shapes, same kernels).
+    kind "reference": the UNMODIFIED reference (`MDM` + `SpacedDiffusion.p_sample_loop`, staged under oracle/_ref by
+    oracle/build_ref.py) through its own public API; kind "port": oracle/dsg_oracle.py when no staged copy exists."""
     from diffusestylegesture_b200.config import ZEGGS
     from diffusestylegesture_b200.synthetic import synthetic_state_dict, synthetic_conditioning
-    from oracle import dsg_oracle as O
+    from oracle import build_ref
     torch.set_num_threads(threads)
     g = ZEGGS
     sd = synthetic_state_dict(g, seed=0)
     y = synthetic_conditioning(g, batch, segment=0)
-    sched = O.Schedule(1000)
-    # the reference draws its noise with torch.randn (gaussian_diffusion.py:542): time THAT, not the numpy Philox
-    # restatement the parity tests use
-    O.noise_tensor = lambda seed, clip_ids, segment, draw, shp: torch.randn((len(clip_ids),) + tuple(shp))
+    shape = (batch, g.njoints, 1, g.n_poses)
+    if build_ref.available():
+        kind = "reference"
+        MDM, gd, SpacedDiffusion, space_timesteps = build_ref.load_reference("zeggs")
+        with open(os.devnull, "w") as devnull:             # the reference constructor prints its configuration
+            old = sys.stdout
+            sys.stdout = devnull
+            try:
+                model = build_ref.make_reference_model(MDM, g, sd)
+            finally:
+                sys.stdout = old
+        diffusion = build_ref.make_reference_diffusion(gd, SpacedDiffusion, space_timesteps)
+        yy = {'style': y['style'], 'seed': y['seed'], 'audio': y['audio'], 'mask_local': torch.ones(1, g.n_poses).bool(),
+              'mask': (torch.zeros([1, 1, 1, g.n_poses]) < 1)}                      # sample.py:226-234
+
+        def run(nsteps):                                    # the call of sample.py:253-264
+            return diffusion.p_sample_loop(model, shape, clip_denoised=False, model_kwargs={'y': yy}, skip_timesteps=1000 - nsteps,
+                                           init_image=None, progress=False, dump_steps=None, noise=None, const_noise=False)
+        what = "the unmodified reference (oracle/_ref: MDM + SpacedDiffusion.p_sample_loop, torch fp32 CPU"
+    else:
+        kind = "port"
+        from oracle import dsg_oracle as O
+        sched = O.Schedule(1000)
+        # the reference draws its noise with torch.randn (gaussian_diffusion.py:542): time THAT, not the numpy Philox
+        # restatement the parity tests use
+        O.noise_tensor = lambda seed, clip_ids, segment, draw, shp: torch.randn((len(clip_ids),) + tuple(shp))
+
+        def run(nsteps):
+            return O.p_sample_loop(sd, g, sched, y, batch, skip_timesteps=1000 - nsteps)
+        what = "oracle/dsg_oracle.py (port of the reference, torch fp32 CPU"
     with torch.no_grad():
-        O.p_sample_loop(sd, g, sched, y, batch, skip_timesteps=1000 - 3)        # warm-up
+        run(3)                                              # warm-up
         t0 = time.perf_counter()
-        O.p_sample_loop(sd, g, sched, y, batch, skip_timesteps=1000 - sample_steps)
+        run(sample_steps)
         dt = time.perf_counter() - t0
     per_step = dt / sample_steps
     clip_seconds = per_step * 1000 * 4
-    return {"value": batch * N_FRAMES / clip_seconds, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": f"{sample_steps} DDPM steps of one 88-frame segment at batch {batch} (oracle/dsg_oracle.py, torch fp32, "
+    return {"value": batch * N_FRAMES / clip_seconds, "unit": UNIT, "cores": threads, "kind": kind,
+            "sample": f"{sample_steps} DDPM steps of one 88-frame segment at batch {batch}: {what}, "
                       f"{threads} threads; {dt:.1f} s), extrapolated linearly to 4 segments x 1000 steps",
-            "ms_per_denoise_step": per_step * 1e3}
+            "ms_per_denoise_step": per_step * 1e3, "batch": batch}
 
 
 WAVLM_FLOP_PER_SEGMENT = 162.5e9      # 70,400 samples -> 219 frames: convs 21.6 + pos-conv 3.7 + 24 layers 137 GFLOP (DESIGN.md)
@@ -219,8 +247,9 @@ def run_reference(args, rank, world):
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": wall / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "ZEGGS 320-frame clips (4 segments x 88 frames), 1000-step DDPM, CPU oracle port of the "
-                                   "reference sampler; each bench step = bounded sample extrapolated", "batch": args.ref_batch},
+            "config": {"workload": "ZEGGS 320-frame clips (4 segments x 88 frames), 1000-step DDPM, the reference sampler on the "
+                                   "host cores (" + cb["kind"] + "); each bench step = bounded sample extrapolated",
+                       "batch": args.ref_batch, "host_threads": threads},
             "cpu_baseline": cb,
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     emit(line)
