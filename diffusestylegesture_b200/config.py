@@ -9,6 +9,7 @@ from dataclasses import dataclass, asdict
 
 VARIANT_ZEGGS_ATTN3 = 3      # cond_mode 'cross_local_attention3_style1' (reference main/model/mdm.py:194-233)
 VARIANT_BEAT_ATTN4 = 4       # cond_mode 'cross_local_attention4_style1' (BEAT-TWH-main/model/mdm.py:187-224)
+VARIANT_BEAT_ATTN5 = 5       # cond_mode 'cross_local_attention5_style1' ("++", BEAT-TWH-main/model/mdm.py:226-264)
 
 
 @dataclass(frozen=True)
@@ -35,7 +36,9 @@ class ModelGeometry:
 
     @property
     def audio_frames(self):      # frames covered by y['audio']
-        return self.n_poses if self.variant == VARIANT_ZEGGS_ATTN3 else self.n_poses - self.n_seed
+        if self.variant == VARIANT_ZEGGS_ATTN3:
+            return self.n_poses
+        return self.n_poses - (2 if self.variant == VARIANT_BEAT_ATTN5 else 1) * self.n_seed
 
     def as_dict(self):
         return asdict(self)
@@ -52,7 +55,12 @@ TWH_PLUS = ModelGeometry(variant=VARIANT_BEAT_ATTN4, njoints=2232, n_poses=150, 
                          latent_dim=512, local_window=15, audio_dim=1435, audio_latent=128,
                          style_in=17, style_latent=512)
 
-PRESETS = {"zeggs": ZEGGS, "beat+": BEAT_PLUS, "twh+": TWH_PLUS}
+# DiffuseStyleGesture++ (cond_mode cross_local_attention5: the last n_seed frames are conditioned on y['seed_last'])
+BEAT_PLUSPLUS = ModelGeometry(variant=VARIANT_BEAT_ATTN5, njoints=2052, n_poses=150, n_seed=30,
+                              latent_dim=384, local_window=15, audio_dim=1434, audio_latent=96,
+                              style_in=2, style_latent=384)
+
+PRESETS = {"zeggs": ZEGGS, "beat+": BEAT_PLUS, "twh+": TWH_PLUS, "beat++": BEAT_PLUSPLUS}
 
 
 def state_dict_spec(g: ModelGeometry):
@@ -101,4 +109,6 @@ def state_dict_spec(g: ModelGeometry):
             (p + "norm2.weight", (D,)),
             (p + "norm2.bias", (D,)),
         ]
+    if g.variant == VARIANT_BEAT_ATTN5:      # the "++" tensors come last (include/dsg.h: DSG_VARIANT_ATTN5)
+        spec += [("embed_text_last.weight", (A, J)), ("embed_text_last.bias", (A,))]
     return spec

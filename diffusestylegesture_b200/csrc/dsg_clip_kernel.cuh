@@ -238,7 +238,8 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const int first_index = P.lp->first_index;
+  const int draw0 = P.lp->k;                               // loop iteration of this launch's first step (dump_steps cuts the loop)
+  const int first_index = P.lp->first_index - draw0;
   const uint32_t key0 = P.lp->key0, key1 = P.lp->key1, segment = P.lp->segment;
 
   const int q4 = warp & 3, sub = warp >> 2;
@@ -417,7 +418,7 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
         if (index == 0 || P.sampler != 0) continue;
         ph.wait(bars, B_ZF);
         for (int q = lane; q < J * T / 4; q += 32)
-          *reinterpret_cast<float4*>(zc + 4 * q) = philox_normal4((uint32_t)q, (uint32_t)(1 + k), cid, segment, key0, key1);
+          *reinterpret_cast<float4*>(zc + 4 * q) = philox_normal4((uint32_t)q, (uint32_t)(1 + draw0 + k), cid, segment, key0, key1);
         fence_async_all();                               // z is read back through the async proxy (bulk copies)
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars[B_ZR]);

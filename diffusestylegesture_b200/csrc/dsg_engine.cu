@@ -133,12 +133,13 @@ static std::vector<size_t> weight_sizes(const dsg_model_desc& d) {
     const size_t per[12] = {3 * D * D, 3 * D, D * D, D, F * D, F, D * F, D, D, D, D, D};
     for (size_t v : per) s.push_back(v);
   }
+  if (d.variant == DSG_VARIANT_ATTN5) { s.push_back(A * J); s.push_back(A); }     // embed_text_last (BEAT-TWH-main/model/mdm.py:95)
   return s;
 }
 
 static int validate_desc(const dsg_model_desc& d) {
-  if (d.variant != DSG_VARIANT_ATTN3 && d.variant != DSG_VARIANT_ATTN4)
-    return dsg_fail(DSG_ERR_UNSUPPORTED, "variant %d: only cross_local_attention3 (3) and 4 are implemented", d.variant);
+  if (d.variant != DSG_VARIANT_ATTN3 && d.variant != DSG_VARIANT_ATTN4 && d.variant != DSG_VARIANT_ATTN5)
+    return dsg_fail(DSG_ERR_UNSUPPORTED, "variant %d: cross_local_attention3 (3), 4 and 5 are implemented", d.variant);
   if (d.njoints <= 0 || d.n_poses <= 0 || d.max_batch <= 0 || d.num_layers <= 0 || d.num_timesteps <= 0)
     return dsg_fail(DSG_ERR_BAD_SHAPE, "non-positive size in descriptor");
   if (d.latent_dim % d.local_heads || d.latent_dim % d.num_heads || (d.latent_dim / d.local_heads) % 2)
@@ -150,8 +151,9 @@ static int validate_desc(const dsg_model_desc& d) {
   if (((long long)d.njoints * d.n_poses) % 4) return dsg_fail(DSG_ERR_BAD_SHAPE, "njoints*n_poses must be a multiple of 4");
   if (d.latent_dim > 512 || d.latent_dim % 32) return dsg_fail(DSG_ERR_BAD_SHAPE, "latent_dim must be a multiple of 32, <= 512");
   if (d.variant == DSG_VARIANT_ATTN3 && d.style_latent >= d.latent_dim) return dsg_fail(DSG_ERR_BAD_SHAPE, "style_latent");
-  if (d.variant == DSG_VARIANT_ATTN4 && d.style_latent != d.latent_dim) return dsg_fail(DSG_ERR_BAD_SHAPE, "style_latent must equal latent_dim for attn4");
+  if (d.variant != DSG_VARIANT_ATTN3 && d.style_latent != d.latent_dim) return dsg_fail(DSG_ERR_BAD_SHAPE, "style_latent must equal latent_dim for attn4 / attn5");
   if (d.n_seed <= 0 || d.n_seed >= d.n_poses) return dsg_fail(DSG_ERR_BAD_SHAPE, "n_seed");
+  if (d.variant == DSG_VARIANT_ATTN5 && 2 * d.n_seed >= d.n_poses) return dsg_fail(DSG_ERR_BAD_SHAPE, "attn5 needs n_poses > 2 n_seed");
   if (d.precision != DSG_PRECISION_FP32 && d.precision != DSG_PRECISION_BF16) return dsg_fail(DSG_ERR_BAD_SHAPE, "precision");
   return DSG_OK;
 }
@@ -171,7 +173,7 @@ extern "C" int dsg_engine_create(const dsg_model_desc* desc, const float* const*
   CUDA_TRY(cudaGetDeviceProperties(&prop, desc->device));
   if (prop.major != 10)
     return dsg_fail(DSG_ERR_BAD_ARCH, "device %d is sm_%d%d; libdsg is built for sm_100a only", desc->device, prop.major, prop.minor);
-  CUDA_TRY(cudaSetDevice(desc->device));
+  DeviceGuard guard(desc->device);
 
   const std::vector<size_t> sizes = weight_sizes(*desc);
   if ((int)sizes.size() != n_weights)
@@ -202,9 +204,9 @@ extern "C" int dsg_engine_create(const dsg_model_desc* desc, const float* const*
   }
 #define TRY_CREATE(x) do { int rc__ = (x); if (rc__) { dsg_engine_destroy(e); return rc__; } } while (0)
   // ---- derived tables
-  float* pe_d = nullptr; float* l1 = nullptr;
-  TRY_CREATE(dalloc(&pe_d, (size_t)NT * D));
-  TRY_CREATE(dalloc(&l1, (size_t)NT * D));
+  TRY_CREATE(dalloc(&e->pe_d, (size_t)NT * D));
+  TRY_CREATE(dalloc(&e->l1, (size_t)NT * D));
+  float* pe_d = e->pe_d; float* l1 = e->l1;
   if (cudaMemcpy(pe_d, pe, (size_t)NT * D * sizeof(float), cudaMemcpyDefault) != cudaSuccess) {
     rc = dsg_fail(DSG_ERR_CUDA, "copy of pe failed"); dsg_engine_destroy(e); return rc; }
   TRY_CREATE(dalloc(&e->te, (size_t)NT * D));
@@ -253,6 +255,7 @@ extern "C" int dsg_engine_create(const dsg_model_desc* desc, const float* const*
   TRY_CREATE(dalloc(&e->x0, (size_t)MB * J * T));
   TRY_CREATE(dalloc(&e->tsel, (size_t)MB));
   TRY_CREATE(dalloc(&e->clip_ids, (size_t)MB));
+  TRY_CREATE(dalloc(&e->noise_ids, (size_t)MB));
   TRY_CREATE(dalloc(&e->d_k, (size_t)1));
   TRY_CREATE(dalloc(&e->d_loop, (size_t)1));
   // opt-in shared memory for the attention kernels
@@ -272,16 +275,18 @@ extern "C" int dsg_engine_create(const dsg_model_desc* desc, const float* const*
   if (cudaDeviceSynchronize() != cudaSuccess) {
     rc = dsg_fail(DSG_ERR_CUDA, "engine setup kernels failed: %s", cudaGetErrorString(cudaGetLastError()));
     dsg_engine_destroy(e); return rc; }
-  cudaFree(pe_d); cudaFree(l1);
+  cudaFree(e->pe_d); cudaFree(e->l1);
+  e->pe_d = nullptr; e->l1 = nullptr;
   *out = e;
   return DSG_OK;
 }
 
 extern "C" void dsg_engine_destroy(dsg_engine* e) {
   if (!e) return;
-  cudaSetDevice(e->d.device);
+  DeviceGuard guard(e->d.device);
   dsg_tc_destroy(e);
-  void* ptrs[] = {e->wslab, e->te, e->TW, e->Wxp, e->bxp, e->cs_local, e->emb1, e->cvec, e->enc, e->cond, e->h, e->xs,
+  for (float* p : e->plms_buf) if (p) cudaFree(p);
+  void* ptrs[] = {e->pe_d, e->l1, e->noise_ids, e->wslab, e->te, e->TW, e->Wxp, e->bxp, e->cs_local, e->emb1, e->cvec, e->enc, e->cond, e->h, e->xs,
                   e->qkv, e->att, e->ff, e->tmp, e->x0, e->tsel, e->clip_ids, e->d_k, e->d_loop, e->coef, e->tmap, e->dbg};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (Stage& s : e->stage) if (s.p) cudaFree(s.p);
@@ -295,12 +300,13 @@ extern "C" void dsg_engine_destroy(dsg_engine* e) {
 extern "C" int dsg_set_schedule(dsg_engine* e, int32_t sampler, int32_t nsteps, const float* coef, const float* qsample,
                                 const int32_t* timestep_map) {
   if (!e || !coef || !qsample || !timestep_map) return dsg_fail(DSG_ERR_BAD_SHAPE, "null argument");
-  if (sampler != DSG_SAMPLER_DDPM && sampler != DSG_SAMPLER_DDIM) return dsg_fail(DSG_ERR_UNSUPPORTED, "sampler %d", sampler);
+  if (sampler != DSG_SAMPLER_DDPM && sampler != DSG_SAMPLER_DDIM && sampler != DSG_SAMPLER_PLMS)
+    return dsg_fail(DSG_ERR_UNSUPPORTED, "sampler %d", sampler);
   if (nsteps <= 0 || nsteps > e->d.num_timesteps) return dsg_fail(DSG_ERR_BAD_SHAPE, "nsteps %d", nsteps);
   for (int i = 0; i < nsteps; ++i)
     if (timestep_map[i] < 0 || timestep_map[i] >= e->d.num_timesteps)
       return dsg_fail(DSG_ERR_BAD_SHAPE, "timestep_map[%d] = %d out of range", i, timestep_map[i]);
-  CUDA_TRY(cudaSetDevice(e->d.device));
+  DeviceGuard guard(e->d.device);
   if (e->coef) cudaFree(e->coef);
   if (e->tmap) cudaFree(e->tmap);
   e->coef = nullptr; e->tmap = nullptr;
@@ -320,14 +326,21 @@ extern "C" int dsg_set_schedule(dsg_engine* e, int32_t sampler, int32_t nsteps, 
 // --------------------------------------------------------------------------------------------------
 extern "C" int dsg_set_conditioning(dsg_engine* e, int32_t B, const float* style, const float* seed, const float* audio,
                                     void* stream) {
+  return dsg_set_conditioning_ex(e, B, style, seed, audio, nullptr, stream);
+}
+
+extern "C" int dsg_set_conditioning_ex(dsg_engine* e, int32_t B, const float* style, const float* seed, const float* audio,
+                                       const float* seed_last, void* stream) {
   if (!e || !style || !seed || !audio) return dsg_fail(DSG_ERR_BAD_SHAPE, "null argument");
+  if ((e->d.variant == DSG_VARIANT_ATTN5) != (seed_last != nullptr))
+    return dsg_fail(DSG_ERR_BAD_SHAPE, "seed_last is required for (and only for) the cross_local_attention5 variant");
   if (B <= 0 || B > e->d.max_batch) return dsg_fail(DSG_ERR_BAD_SHAPE, "batch %d outside 1..%d", B, e->d.max_batch);
-  CUDA_TRY(cudaSetDevice(e->d.device));
+  DeviceGuard guard(e->d.device);
   cudaStream_t st = (cudaStream_t)stream;
   const dsg_model_desc& d = e->d;
   const int D = d.latent_dim, J = d.njoints, T = d.n_poses, A = d.audio_latent, NS = d.n_seed;
   const int ld2 = 2 * D + A;
-  const int Ta = d.variant == DSG_VARIANT_ATTN3 ? T : T - NS;
+  const int Ta = d.variant == DSG_VARIANT_ATTN3 ? T : (d.variant == DSG_VARIANT_ATTN4 ? T - NS : T - 2 * NS);
   const void *sty_d, *seed_d, *aud_d;
   int rc;
   if ((rc = dev_in(e, 0, style, (size_t)B * d.style_in * sizeof(float), st, &sty_d))) return rc;
@@ -355,6 +368,16 @@ extern "C" int dsg_set_conditioning(dsg_engine* e, int32_t B, const float* style
     GemmF32Args g2 = gemm_plain(au, d.audio_dim, e->w[W_AUD_W], d.audio_dim, e->enc, A, B * Ta, A, d.audio_dim, e->w[W_AUD_B], 0);
     g2.cm = RowMap{Ta, NS, (long long)T * A, A};
     TRY(launch_gemm_f32(e, g2, false, false, st));
+    if (d.variant == DSG_VARIANT_ATTN5) {
+      // embed_text_last on each frame of y['seed_last'] -> enc[:, n_seed + Ta:]   (BEAT-TWH-main/model/mdm.py:229-230)
+      const void* last_d;
+      if ((rc = dev_in(e, 6, seed_last, (size_t)B * J * NS * sizeof(float), st, &last_d))) return rc;
+      const size_t wl = e->w.size() - 2;
+      GemmF32Args g3 = gemm_plain((const float*)last_d, 0, e->w[wl], J, e->enc, A, B * NS, A, J, e->w[wl + 1], 0);
+      g3.am = RowMap{NS, 0, (long long)J * NS, 1}; g3.a_kstride = NS;
+      g3.cm = RowMap{NS, NS + Ta, (long long)T * A, A};
+      TRY(launch_gemm_f32(e, g3, true, false, st));
+    }
   }
   // cvec[b] = W_tok * emb1[b] + (W_x b_pose + b_2)
   TRY(launch_gemm_f32(e, gemm_plain(e->emb1, D, e->w[W_IN2_W], ld2, e->cvec, D, B, D, D, e->bxp, 0), false, false, st));
@@ -456,7 +479,7 @@ extern "C" int dsg_denoise(dsg_engine* e, int32_t B, const float* x, const int32
   if (e->cond_batch != B) return dsg_fail(DSG_ERR_STATE, "dsg_set_conditioning was called for batch %d, not %d", e->cond_batch, B);
   for (int b = 0; b < B; ++b)
     if (timesteps[b] < 0 || timesteps[b] >= e->d.num_timesteps) return dsg_fail(DSG_ERR_BAD_SHAPE, "timestep %d out of range", timesteps[b]);
-  CUDA_TRY(cudaSetDevice(e->d.device));
+  DeviceGuard guard(e->d.device);
   cudaStream_t st = (cudaStream_t)stream;
   const size_t bytes = (size_t)B * e->d.njoints * e->d.n_poses * sizeof(float);
   const void* xd;
@@ -485,7 +508,7 @@ int elementwise_grid(const dsg_engine* e, long long quads) {
 int launch_posterior(dsg_engine* e, int B, float* x, const float* x0, StepRef step, int index_imm, int draw_imm,
                      uint64_t seed, int segment, cudaStream_t st) {
   PosteriorArgs a;
-  a.x = x; a.x0 = x0; a.coef = e->coef; a.clip_ids = e->clip_ids; a.step = step; a.index_imm = index_imm; a.draw_imm = draw_imm;
+  a.x = x; a.x0 = x0; a.coef = e->coef; a.clip_ids = e->noise_ids; a.step = step; a.index_imm = index_imm; a.draw_imm = draw_imm;
   a.sampler = e->sampler; a.B = B; a.per_clip = (long long)e->d.njoints * e->d.n_poses;
   a.k0 = (uint32_t)(seed & 0xffffffffu); a.k1 = (uint32_t)(seed >> 32); a.segment = (uint32_t)segment;
   posterior_step_kernel<<<elementwise_grid(e, (a.per_clip >> 2) * B), 256, 0, st>>>(a);
@@ -494,10 +517,18 @@ int launch_posterior(dsg_engine* e, int B, float* x, const float* x0, StepRef st
   return DSG_OK;
 }
 
-static int upload_clip_ids(dsg_engine* e, int B, const int64_t* clip_ids, cudaStream_t st) {
-  e->h_clip_ids.resize(B);
-  for (int b = 0; b < B; ++b) e->h_clip_ids[b] = clip_ids ? (long long)clip_ids[b] : (long long)b;
+// clip ids key the Philox counter as 32-bit words: ids outside [0, 2^32) would alias another clip's stream and are rejected.
+// const_noise: the per-step draws of every clip use clip 0's key (noise[[0]].repeat(...), gaussian_diffusion.py:544-545).
+static int upload_clip_ids(dsg_engine* e, int B, const int64_t* clip_ids, bool const_noise, cudaStream_t st) {
+  e->h_clip_ids.resize(2 * (size_t)B);
+  for (int b = 0; b < B; ++b) {
+    const long long id = clip_ids ? (long long)clip_ids[b] : (long long)b;
+    if (id < 0 || id > 0xFFFFFFFFll) return dsg_fail(DSG_ERR_BAD_SHAPE, "clip id %lld outside [0, 2^32)", id);
+    e->h_clip_ids[b] = id;
+  }
+  for (int b = 0; b < B; ++b) e->h_clip_ids[B + b] = const_noise ? e->h_clip_ids[0] : e->h_clip_ids[b];
   CUDA_TRY(cudaMemcpyAsync(e->clip_ids, e->h_clip_ids.data(), B * sizeof(long long), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(e->noise_ids, e->h_clip_ids.data() + B, B * sizeof(long long), cudaMemcpyHostToDevice, st));
   return DSG_OK;
 }
 
@@ -507,11 +538,11 @@ extern "C" int dsg_posterior_step(dsg_engine* e, int32_t B, float* x, const floa
   if (!e->coef) return dsg_fail(DSG_ERR_STATE, "dsg_set_schedule has not been called");
   if (B <= 0 || B > e->d.max_batch) return dsg_fail(DSG_ERR_BAD_SHAPE, "batch %d outside 1..%d", B, e->d.max_batch);
   if (index < 0 || index >= e->nsteps) return dsg_fail(DSG_ERR_BAD_SHAPE, "index %d outside 0..%d", index, e->nsteps - 1);
-  CUDA_TRY(cudaSetDevice(e->d.device));
+  DeviceGuard guard(e->d.device);
   cudaStream_t st = (cudaStream_t)stream;
   const size_t bytes = (size_t)B * e->d.njoints * e->d.n_poses * sizeof(float);
   int rc;
-  if ((rc = upload_clip_ids(e, B, clip_ids, st))) return rc;
+  if ((rc = upload_clip_ids(e, B, clip_ids, false, st))) return rc;
   const void* x0d;
   if ((rc = dev_in(e, 4, x0, bytes, st, &x0d))) return rc;
   const bool xdev = is_device_ptr(x);
@@ -525,20 +556,86 @@ extern "C" int dsg_posterior_step(dsg_engine* e, int32_t B, float* x, const floa
   return DSG_OK;
 }
 
+// PLMS (plms_sample_loop_progressive, gaussian_diffusion.py:1136-1200): one denoiser call per step (two on the first),
+// the multistep combination in plms_update_kernel.  The denoiser runs through dsg_denoise_step (either precision).
+static int plms_run(dsg_engine* e, int B, float* xd, int k0, int n_run, int first_index, int order, int* hist_len, uint64_t seed,
+                    int segment, cudaStream_t st) {
+  const long long per_clip = (long long)e->d.njoints * e->d.n_poses;
+  const size_t cap = (size_t)e->d.max_batch * per_clip;
+  for (float*& p : e->plms_buf) if (!p) TRY(dalloc(&p, cap));
+  float* tmp = e->plms_buf[4]; float* x0b = e->plms_buf[5];
+  const uint32_t key0 = (uint32_t)(seed & 0xffffffffu), key1 = (uint32_t)(seed >> 32);
+  PlmsArgs a;
+  a.x = xd; a.x0 = e->x0; a.x0b = x0b; a.tmp = tmp; a.coef = e->coef; a.total4 = (per_clip >> 2) * B;
+  const int grid = elementwise_grid(e, a.total4);
+  for (int k = k0; k < k0 + n_run; ++k) {
+    const int index = first_index - k;
+    const StepRef step{nullptr, k, first_index, key0, key1, (uint32_t)segment};
+    TRY(dsg_denoise_step(e, B, xd, nullptr, step, e->x0, st));
+    a.index = index;
+    const int slot = k % order;                      // ring of `order` eps slots: newest at `slot`
+    for (int i = 0; i < 4; ++i) a.hist[i] = e->plms_buf[((slot - i) % order + order) % order];
+    if (*hist_len == 0) {                            // old_out is None: pseudo improved Euler (:1061-1067)
+      if (index == 0) return dsg_fail(DSG_ERR_BAD_SHAPE, "plms: the first step needs a second model call at t - 1 (skip_timesteps leaves one step)");
+      a.mode = 0; a.n = 1;
+      plms_update_kernel<<<grid, 256, 0, st>>>(a);
+      e->launches++;
+      const StepRef step2{nullptr, k + 1, first_index, key0, key1, (uint32_t)segment};
+      TRY(dsg_denoise_step(e, B, tmp, nullptr, step2, x0b, st));
+      a.mode = 1;
+      plms_update_kernel<<<grid, 256, 0, st>>>(a);
+      e->launches++;
+      *hist_len = 1;
+    } else {                                         // Adams-Bashforth (:1068-1086), then pop(0) when len >= order (:1088-1089)
+      const int len = *hist_len + 1;
+      a.mode = 2; a.n = len < order ? len : order;
+      plms_update_kernel<<<grid, 256, 0, st>>>(a);
+      e->launches++;
+      *hist_len = len >= order ? len - 1 : len;
+    }
+    CUDA_TRY(cudaGetLastError());
+  }
+  return DSG_OK;
+}
+
 extern "C" int dsg_sample_loop(dsg_engine* e, int32_t B, float* x, int32_t noise_given, uint64_t seed,
                                const int64_t* clip_ids, int32_t segment, int32_t skip_timesteps, const float* init_image,
                                void* stream) {
+  return dsg_sample_loop_ex(e, B, x, noise_given, seed, clip_ids, segment, skip_timesteps, init_image, nullptr, stream);
+}
+
+extern "C" int dsg_sample_loop_ex(dsg_engine* e, int32_t B, float* x, int32_t noise_given, uint64_t seed,
+                                  const int64_t* clip_ids, int32_t segment, int32_t skip_timesteps, const float* init_image,
+                                  const dsg_loop_opts* opts, void* stream) {
   if (!e || !x) return dsg_fail(DSG_ERR_BAD_SHAPE, "null argument");
   if (!e->coef) return dsg_fail(DSG_ERR_STATE, "dsg_set_schedule has not been called");
   if (B <= 0 || B > e->d.max_batch) return dsg_fail(DSG_ERR_BAD_SHAPE, "batch %d outside 1..%d", B, e->d.max_batch);
   if (e->cond_batch != B) return dsg_fail(DSG_ERR_STATE, "dsg_set_conditioning was called for batch %d, not %d", e->cond_batch, B);
   if (skip_timesteps < 0 || skip_timesteps >= e->nsteps) return dsg_fail(DSG_ERR_BAD_SHAPE, "skip_timesteps %d", skip_timesteps);
-  CUDA_TRY(cudaSetDevice(e->d.device));
+  const int n_run = e->nsteps - skip_timesteps;
+  const int first_index = n_run - 1;
+  const bool const_noise = opts && (opts->flags & DSG_LOOP_CONST_NOISE);
+  const int n_dump = opts ? opts->n_dump : 0;
+  const int order = (opts && opts->plms_order) ? opts->plms_order : 2;
+  if (opts && (opts->flags & ~DSG_LOOP_CONST_NOISE)) return dsg_fail(DSG_ERR_UNSUPPORTED, "unknown loop flags 0x%x", opts->flags);
+  if (n_dump < 0 || (n_dump > 0 && (!opts->dump_iters || !opts->dump_out))) return dsg_fail(DSG_ERR_BAD_SHAPE, "dump_iters / dump_out");
+  for (int i = 0; i < n_dump; ++i)
+    if (opts->dump_iters[i] < 0 || opts->dump_iters[i] >= n_run || (i > 0 && opts->dump_iters[i] <= opts->dump_iters[i - 1]))
+      return dsg_fail(DSG_ERR_BAD_SHAPE, "dump_iters must be ascending loop iterations in [0, %d)", n_run);
+  if (e->sampler == DSG_SAMPLER_PLMS) {
+    if (order < 2 || order > 4) return dsg_fail(DSG_ERR_BAD_SHAPE, "plms order %d: 2..4 (order 1 fails inside the reference, "
+                                                "gaussian_diffusion.py:1069, and values outside 1..4 raise there)", order);
+    if (const_noise) return dsg_fail(DSG_ERR_UNSUPPORTED, "plms_sample_loop has no const_noise option");
+  } else if (e->sampler == DSG_SAMPLER_DDIM && (const_noise || n_dump)) {
+    return dsg_fail(DSG_ERR_UNSUPPORTED, "ddim_sample_loop raises NotImplementedError for dump_steps / const_noise "
+                    "(gaussian_diffusion.py:913-916)");
+  }
+  DeviceGuard guard(e->d.device);
   cudaStream_t st = (cudaStream_t)stream;
   const long long per_clip = (long long)e->d.njoints * e->d.n_poses;
   const size_t bytes = (size_t)B * per_clip * sizeof(float);
   int rc;
-  if ((rc = upload_clip_ids(e, B, clip_ids, st))) return rc;
+  if ((rc = upload_clip_ids(e, B, clip_ids, const_noise, st))) return rc;
   const bool xdev = is_device_ptr(x);
   float* xd = x;
   if (!xdev) {
@@ -546,8 +643,6 @@ extern "C" int dsg_sample_loop(dsg_engine* e, int32_t B, float* x, int32_t noise
     xd = (float*)e->stage[3].p;
     if (noise_given) CUDA_TRY(cudaMemcpyAsync(xd, x, bytes, cudaMemcpyHostToDevice, st));
   }
-  const int n_run = e->nsteps - skip_timesteps;
-  const int first_index = n_run - 1;
   const void* init_d = nullptr;
   if (init_image && (rc = dev_in(e, 4, init_image, bytes, st, &init_d))) return rc;
   // x_T (th.randn, gaussian_diffusion.py:704) and q_sample for skip_timesteps / init_image (:706-713)
@@ -565,9 +660,23 @@ extern "C" int dsg_sample_loop(dsg_engine* e, int32_t B, float* x, int32_t noise
     e->launches++;
     CUDA_TRY(cudaGetLastError());
   }
-  if ((rc = dsg_run_steps(e, B, xd, n_run, first_index, seed, segment, st))) return rc;
+  // the loop, cut at the dump points (dump_steps: `if i in dump_steps: dump.append(deepcopy(sample))`, :664-665)
+  int k0 = 0, hist_len = 0;
+  for (int piece = 0; piece <= n_dump; ++piece) {
+    const int k1 = piece < n_dump ? opts->dump_iters[piece] + 1 : n_run;
+    if (k1 > k0) {
+      if (e->sampler == DSG_SAMPLER_PLMS) rc = plms_run(e, B, xd, k0, k1 - k0, first_index, order, &hist_len, seed, segment, st);
+      else rc = dsg_run_steps(e, B, xd, k0, k1 - k0, first_index, seed, segment, st);
+      if (rc) return rc;
+    }
+    if (piece < n_dump)
+      CUDA_TRY(cudaMemcpyAsync(opts->dump_out + (size_t)piece * B * per_clip, xd, bytes, cudaMemcpyDefault, st));
+    k0 = k1;
+  }
   if (!xdev) {
     CUDA_TRY(cudaMemcpyAsync(x, xd, bytes, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+  } else if (n_dump > 0 && !is_device_ptr(opts->dump_out)) {
     CUDA_TRY(cudaStreamSynchronize(st));
   }
   return DSG_OK;
@@ -575,9 +684,9 @@ extern "C" int dsg_sample_loop(dsg_engine* e, int32_t B, float* x, int32_t noise
 
 // The hot loop (gaussian_diffusion.py:721-740): n_run x (denoiser + posterior).  Plain stream launches here;
 // dsg_tc.cu overrides with a CUDA-graph replay when the tensor-core path is active.
-int dsg_run_steps(dsg_engine* e, int B, float* xd, int n_run, int first_index, uint64_t seed, int segment, cudaStream_t st) {
-  if (e->d.precision == DSG_PRECISION_BF16) return dsg_tc_run_steps(e, B, xd, n_run, first_index, seed, segment, st);
-  for (int k = 0; k < n_run; ++k) {
+int dsg_run_steps(dsg_engine* e, int B, float* xd, int k0, int n_run, int first_index, uint64_t seed, int segment, cudaStream_t st) {
+  if (e->d.precision == DSG_PRECISION_BF16) return dsg_tc_run_steps(e, B, xd, k0, n_run, first_index, seed, segment, st);
+  for (int k = k0; k < k0 + n_run; ++k) {
     const StepRef step{nullptr, k, first_index};
     TRY(denoise_f32(e, B, xd, nullptr, step, e->x0, st));
     PROF(e, PT_POSTERIOR, st, launch_posterior(e, B, xd, e->x0, step, -1, 0, seed, segment, st));
@@ -586,10 +695,10 @@ int dsg_run_steps(dsg_engine* e, int B, float* xd, int n_run, int first_index, u
   return DSG_OK;
 }
 
-int dsg_upload_loop_params(dsg_engine* e, int first_index, uint64_t seed, int segment, cudaStream_t st) {
+int dsg_upload_loop_params(dsg_engine* e, int k0, int first_index, uint64_t seed, int segment, cudaStream_t st) {
   LoopParams lp;
   memset(&lp, 0, sizeof lp);
-  lp.k = 0; lp.first_index = first_index;
+  lp.k = k0; lp.first_index = first_index;
   lp.key0 = (uint32_t)(seed & 0xffffffffu); lp.key1 = (uint32_t)(seed >> 32); lp.segment = (uint32_t)segment;
   CUDA_TRY(cudaMemcpyAsync(e->d_loop, &lp, sizeof lp, cudaMemcpyHostToDevice, st));   // pageable source: staged before return
   return DSG_OK;
@@ -599,7 +708,7 @@ extern "C" int dsg_stitch_segment(dsg_engine* e, int32_t B, const float* prev_ta
                                   void* stream) {
   if (!e || !prev_tail || !sample) return dsg_fail(DSG_ERR_BAD_SHAPE, "null argument");
   if (B <= 0 || B > e->d.max_batch) return dsg_fail(DSG_ERR_BAD_SHAPE, "batch %d outside 1..%d", B, e->d.max_batch);
-  CUDA_TRY(cudaSetDevice(e->d.device));
+  DeviceGuard guard(e->d.device);
   cudaStream_t st = (cudaStream_t)stream;
   const size_t sb = (size_t)B * e->d.njoints * e->d.n_poses * sizeof(float);
   const size_t tb = (size_t)B * e->d.njoints * e->d.n_seed * sizeof(float);
@@ -626,7 +735,7 @@ extern "C" int64_t dsg_kernel_launch_count(const dsg_engine* e) { return e ? e->
 
 extern "C" int64_t dsg_debug_read(dsg_engine* e, const char* name, int32_t B, float* dst, int64_t capacity) {
   if (!e || !name) return dsg_fail(DSG_ERR_BAD_SHAPE, "null argument");
-  CUDA_TRY(cudaSetDevice(e->d.device));
+  DeviceGuard guard(e->d.device);
   const int D = e->d.latent_dim, S = e->S, T = e->d.n_poses;
   const size_t slot_elems = (size_t)e->d.max_batch * S * D;
   if (!strcmp(name, "enable")) {
@@ -676,7 +785,7 @@ extern "C" int64_t dsg_debug_read(dsg_engine* e, const char* name, int32_t B, fl
 
 extern "C" int dsg_profile(dsg_engine* e, int32_t enable) {
   if (!e) return dsg_fail(DSG_ERR_BAD_SHAPE, "null argument");
-  CUDA_TRY(cudaSetDevice(e->d.device));
+  DeviceGuard guard(e->d.device);
   if (e->profiling) prof_collect(e);
   if (enable == 1 && !e->profiling) { for (int i = 0; i < PT_COUNT; ++i) { e->prof_ms[i] = 0; e->prof_n[i] = 0; } }
   e->profiling = enable != 0;

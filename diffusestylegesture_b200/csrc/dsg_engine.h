@@ -57,8 +57,11 @@ struct dsg_engine {
   // workspace (fp32 path)
   float *h = nullptr, *xs = nullptr, *qkv = nullptr, *att = nullptr, *ff = nullptr, *tmp = nullptr, *x0 = nullptr;
   int* tsel = nullptr;
-  long long* clip_ids = nullptr;
+  long long* clip_ids = nullptr;     // keys of the x_T draw (one stream per clip)
+  long long* noise_ids = nullptr;    // keys of the per-step draws: == clip_ids, or clip_ids[0] everywhere (const_noise)
   std::vector<long long> h_clip_ids;
+  float* plms_buf[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // PLMS: 4 eps slots, mean_pred, second x0 (lazy)
+  float *pe_d = nullptr, *l1 = nullptr;     // create-time scratch (freed by destroy on every path)
   LoopParams* d_loop = nullptr;      // device loop state for graph replay
   int* d_k = nullptr;
   size_t smem_self = 0, smem_local = 0;
@@ -100,11 +103,19 @@ int launch_local_attention(dsg_engine* e, int B, const float* h, long long h_cli
 int launch_self_attention(dsg_engine* e, int B, const float* qkv, float* out, cudaStream_t st);
 int launch_self_attention_bf16(dsg_engine* e, int B, const __nv_bfloat16* qkv, __nv_bfloat16* out, cudaStream_t st);
 int elementwise_grid(const dsg_engine* e, long long quads);
-int dsg_upload_loop_params(dsg_engine* e, int first_index, uint64_t seed, int segment, cudaStream_t st);
+int dsg_upload_loop_params(dsg_engine* e, int k0, int first_index, uint64_t seed, int segment, cudaStream_t st);
+
+// Entry points run on the engine's device and restore the caller's current device on return.
+struct DeviceGuard {
+  int prev = -1, cur = -1;
+  explicit DeviceGuard(int dev) : cur(dev) { if (cudaGetDevice(&prev) != cudaSuccess) prev = -1; if (prev != dev) cudaSetDevice(dev); }
+  ~DeviceGuard() { if (prev >= 0 && prev != cur) cudaSetDevice(prev); }
+};
 int launch_posterior(dsg_engine* e, int B, float* x, const float* x0, StepRef step, int index_imm, int draw_imm,
                      uint64_t seed, int segment, cudaStream_t st);
 int dsg_denoise_step(dsg_engine* e, int B, const float* x, const int* tsel, StepRef step, float* out, cudaStream_t st);
-int dsg_run_steps(dsg_engine* e, int B, float* xd, int n_run, int first_index, uint64_t seed, int segment, cudaStream_t st);
+// loop iterations k0 .. k0 + n_run - 1 (iteration k: sampler index first_index - k, noise draw 1 + k)
+int dsg_run_steps(dsg_engine* e, int B, float* xd, int k0, int n_run, int first_index, uint64_t seed, int segment, cudaStream_t st);
 
 // tensor-core path (dsg_tc.cu)
 int dsg_tc_create(dsg_engine* e);
@@ -112,4 +123,4 @@ void dsg_tc_destroy(dsg_engine* e);
 const float* dsg_tc_h(dsg_engine* e);
 const long long* dsg_tc_clip_prof(dsg_engine* e);
 int dsg_tc_denoise(dsg_engine* e, int B, const float* x, const int* tsel, StepRef step, float* out, cudaStream_t st);
-int dsg_tc_run_steps(dsg_engine* e, int B, float* xd, int n_run, int first_index, uint64_t seed, int segment, cudaStream_t st);
+int dsg_tc_run_steps(dsg_engine* e, int B, float* xd, int k0, int n_run, int first_index, uint64_t seed, int segment, cudaStream_t st);

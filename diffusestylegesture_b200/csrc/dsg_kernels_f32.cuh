@@ -359,6 +359,69 @@ __global__ void __launch_bounds__(256) posterior_step_kernel(const PosteriorArgs
   }
 }
 
+// PLMS update (plms_sample, gaussian_diffusion.py:1005-1103), fp32 with the reference's op order.  Coefficient rows are the
+// DDIM ones: c = { sqrt_recip_abar, sqrt_recipm1_abar, sqrt(abar_prev), sqrt(1 - abar_prev) } at the step's index.
+//   mode 0  first step, stage A: eps = (c.x x - x0) / c.y -> hist[0];  tmp = x0 c.z + c.w eps          (:1061-1063)
+//   mode 1  first step, stage B: eps2 from (tmp, x0b) with the row of index - 1; eps' = (eps + eps2) / 2 (:1064-1067)
+//   mode 2  Adams-Bashforth of order `n` over hist[0] (newest, written here) .. hist[n-1]                 (:1068-1086)
+// then x <- index != 0 ? mean_pred : x0                                                                   (:1091-1093)
+struct PlmsArgs {
+  float* x; const float* x0; const float* x0b; float* hist[4]; float* tmp;
+  const float4* coef; int index, mode, n; long long total4;
+};
+DSG_DEVINL float plms_eps(const float4 c, float xt, float x0) { return __fdiv_rn(__fsub_rn(__fmul_rn(c.x, xt), x0), c.y); }
+DSG_DEVINL float plms_out(const float4 c, float xt, float x0, float ep, bool nz) {
+  const float pred = __fsub_rn(__fmul_rn(c.x, xt), __fmul_rn(c.y, ep));
+  const float mean = __fadd_rn(__fmul_rn(pred, c.z), __fmul_rn(c.w, ep));
+  return nz ? mean : x0;
+}
+__global__ void __launch_bounds__(256) plms_update_kernel(const PlmsArgs a) {
+  const float4 c = a.coef[a.index];
+  const float4 cp = a.coef[a.index > 0 ? a.index - 1 : 0];
+  const bool nz = a.index != 0;
+  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < a.total4; g += (long long)gridDim.x * blockDim.x) {
+    const float4 xt4 = reinterpret_cast<const float4*>(a.x)[g];
+    const float4 x04 = reinterpret_cast<const float4*>(a.x0)[g];
+    const float xt[4] = {xt4.x, xt4.y, xt4.z, xt4.w}, x0[4] = {x04.x, x04.y, x04.z, x04.w};
+    float o[4], e[4];
+    if (a.mode == 0) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { e[i] = plms_eps(c, xt[i], x0[i]); o[i] = __fadd_rn(__fmul_rn(x0[i], c.z), __fmul_rn(c.w, e[i])); }
+      reinterpret_cast<float4*>(a.hist[0])[g] = make_float4(e[0], e[1], e[2], e[3]);
+      reinterpret_cast<float4*>(a.tmp)[g] = make_float4(o[0], o[1], o[2], o[3]);
+      continue;
+    }
+    if (a.mode == 1) {
+      const float4 t4 = reinterpret_cast<const float4*>(a.tmp)[g], b4 = reinterpret_cast<const float4*>(a.x0b)[g];
+      const float4 h4 = reinterpret_cast<const float4*>(a.hist[0])[g];
+      const float tm[4] = {t4.x, t4.y, t4.z, t4.w}, xb[4] = {b4.x, b4.y, b4.z, b4.w}, h[4] = {h4.x, h4.y, h4.z, h4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float e2 = plms_eps(cp, tm[i], xb[i]);
+        o[i] = plms_out(c, xt[i], x0[i], __fdiv_rn(__fadd_rn(h[i], e2), 2.0f), nz);
+      }
+    } else {
+      float h1[4] = {0, 0, 0, 0}, h2[4] = {0, 0, 0, 0}, h3[4] = {0, 0, 0, 0};
+      if (a.n > 1) { const float4 t = reinterpret_cast<const float4*>(a.hist[1])[g]; h1[0] = t.x; h1[1] = t.y; h1[2] = t.z; h1[3] = t.w; }
+      if (a.n > 2) { const float4 t = reinterpret_cast<const float4*>(a.hist[2])[g]; h2[0] = t.x; h2[1] = t.y; h2[2] = t.z; h2[3] = t.w; }
+      if (a.n > 3) { const float4 t = reinterpret_cast<const float4*>(a.hist[3])[g]; h3[0] = t.x; h3[1] = t.y; h3[2] = t.z; h3[3] = t.w; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        e[i] = plms_eps(c, xt[i], x0[i]);
+        float ep;
+        if (a.n == 1) ep = e[i];
+        else if (a.n == 2) ep = __fdiv_rn(__fsub_rn(__fmul_rn(3.0f, e[i]), h1[i]), 2.0f);
+        else if (a.n == 3) ep = __fdiv_rn(__fadd_rn(__fsub_rn(__fmul_rn(23.0f, e[i]), __fmul_rn(16.0f, h1[i])), __fmul_rn(5.0f, h2[i])), 12.0f);
+        else ep = __fdiv_rn(__fsub_rn(__fadd_rn(__fsub_rn(__fmul_rn(55.0f, e[i]), __fmul_rn(59.0f, h1[i])), __fmul_rn(37.0f, h2[i])),
+                                     __fmul_rn(9.0f, h3[i])), 24.0f);
+        o[i] = plms_out(c, xt[i], x0[i], ep, nz);
+      }
+      reinterpret_cast<float4*>(a.hist[0])[g] = make_float4(e[0], e[1], e[2], e[3]);
+    }
+    reinterpret_cast<float4*>(a.x)[g] = make_float4(o[0], o[1], o[2], o[3]);
+  }
+}
+
 // x_T ~ N(0, I): draw 0 of the stream (th.randn(*shape), gaussian_diffusion.py:704), optionally followed by
 // q_sample(init_image, t0, noise) (:236-254, 706-713): x = sa * init + sb * noise.
 __global__ void __launch_bounds__(256) init_noise_kernel(float* x, const float* init, int has_noise, float sa, float sb,

@@ -21,7 +21,7 @@ using bf16 = __nv_bfloat16;
 using namespace tc;
 
 struct dsg_tc_state {
-  int Jpad = 0, Rpad = 0;
+  int Jpad = 0, Rpad = 0, bn_d = 256;
   bf16 *Wxp = nullptr, *Wout = nullptr;
   std::vector<bf16*> Wqkv, Wo, W1, W2;
   bf16 *xb = nullptr, *xsb = nullptr, *qkvb = nullptr, *attb = nullptr, *ffb = nullptr;
@@ -104,12 +104,12 @@ static int clip_setup(dsg_engine* e) {
   return DSG_OK;
 }
 
-static int clip_run(dsg_engine* e, int B, float* xd, int n_run, int first_index, uint64_t seed, int segment, cudaStream_t st) {
+static int clip_run(dsg_engine* e, int B, float* xd, int k0, int n_run, int first_index, uint64_t seed, int segment, cudaStream_t st) {
   dsg_tc_state* t = e->tc;
-  TRY(dsg_upload_loop_params(e, first_index, seed, segment, st));
+  TRY(dsg_upload_loop_params(e, k0, first_index, seed, segment, st));
   clip::ClipParams p;
   p.x = xd; p.xa = t->xa; p.z = t->z; p.cond = e->cond; p.emb1 = e->emb1; p.te = e->te; p.TW = e->TW; p.cs = e->cs_local;
-  p.lparams = t->lparams; p.bout = t->bout; p.coef = e->coef; p.tmap = e->tmap; p.clip_ids = e->clip_ids; p.lp = e->d_loop;
+  p.lparams = t->lparams; p.bout = t->bout; p.coef = e->coef; p.tmap = e->tmap; p.clip_ids = e->noise_ids; p.lp = e->d_loop;
   p.B = B; p.n_run = n_run; p.sampler = e->sampler;
   p.prof = getenv("DSG_CLIP_PROF") ? t->prof : nullptr;
   p.dbg = e->dbg; p.dbg_slot = (long long)e->d.max_batch * e->S * e->d.latent_dim; p.debug = e->debug ? 1 : 0;
@@ -126,9 +126,10 @@ static int clip_run(dsg_engine* e, int B, float* xd, int n_run, int first_index,
 // ---------------------------------------------------------------------------------------------------
 int dsg_tc_create(dsg_engine* e) {
   const dsg_model_desc& d = e->d;
-  if (d.latent_dim != 256)
-    return dsg_fail(DSG_ERR_UNSUPPORTED, "DSG_PRECISION_BF16 currently covers latent_dim 256 (ZEGGS); D = %d runs on the fp32 engine",
-                    d.latent_dim);
+  // a LayerNorm row must fit one CTA's accumulator: D = 256 (ZEGGS), 384 (BEAT "+"), 512 (TWH "+")
+  if (d.latent_dim != 256 && d.latent_dim != 384 && d.latent_dim != 512)
+    return dsg_fail(DSG_ERR_UNSUPPORTED, "DSG_PRECISION_BF16 covers latent_dim 256 / 384 / 512 (the reference's presets); D = %d runs "
+                    "on the fp32 engine", d.latent_dim);
   if (d.ff_size % 256) return dsg_fail(DSG_ERR_UNSUPPORTED, "ff_size must be a multiple of 256 for the bf16 path");
   dsg_tc_state* t = new dsg_tc_state();
   e->tc = t;
@@ -140,6 +141,10 @@ int dsg_tc_create(dsg_engine* e) {
   TRY(dalloc0(&t->Wout, (size_t)Jpad * D));
   TRY(pack_w(e->Wxp, t->Wxp, D, J, J, D, Jpad));
   TRY(pack_w(e->w[W_OUT_W], t->Wout, J, D, D, Jpad, D));
+  // tile widths by latent_dim: D-wide outputs (input GEMM, in_proj) in 256- or 128-column tiles; the LayerNorm GEMMs
+  // (out_proj, linear2) in ONE D-wide tile whose B operand arrives as boxes of D (256) or D/2 (384, 512) rows
+  const int bn_d = (D % 256 == 0) ? 256 : 128, box_ln = (D > 256) ? D / 2 : D;
+  t->bn_d = bn_d;
   t->Wqkv.resize(L); t->Wo.resize(L); t->W1.resize(L); t->W2.resize(L);
   t->tm_Wqkv.resize(L); t->tm_Wo.resize(L); t->tm_W1.resize(L); t->tm_W2.resize(L);
   for (int l = 0; l < L; ++l) {
@@ -148,10 +153,10 @@ int dsg_tc_create(dsg_engine* e) {
     TRY(dalloc0(&t->Wo[l], (size_t)D * D));       TRY(pack_w(w[L_OUTPROJ_W], t->Wo[l], D, D, D, D, D));
     TRY(dalloc0(&t->W1[l], (size_t)F * D));       TRY(pack_w(w[L_FF1_W], t->W1[l], F, D, D, F, D));
     TRY(dalloc0(&t->W2[l], (size_t)D * F));       TRY(pack_w(w[L_FF2_W], t->W2[l], D, F, F, D, F));
-    TRY(make_tmap(&t->tm_Wqkv[l], t->Wqkv[l], 3 * D, D, 256));
-    TRY(make_tmap(&t->tm_Wo[l], t->Wo[l], D, D, 256));
+    TRY(make_tmap(&t->tm_Wqkv[l], t->Wqkv[l], 3 * D, D, bn_d));
+    TRY(make_tmap(&t->tm_Wo[l], t->Wo[l], D, D, box_ln));
     TRY(make_tmap(&t->tm_W1[l], t->W1[l], F, D, 256));
-    TRY(make_tmap(&t->tm_W2[l], t->W2[l], D, F, 256));
+    TRY(make_tmap(&t->tm_W2[l], t->W2[l], D, F, box_ln));
   }
   TRY(dalloc0(&t->xb, (size_t)Rpad * Jpad));
   TRY(dalloc0(&t->xsb, (size_t)Rpad * D));
@@ -165,7 +170,7 @@ int dsg_tc_create(dsg_engine* e) {
   TRY(make_tmap(&t->tm_xsb, t->xsb, Rpad, D, BM));
   TRY(make_tmap(&t->tm_attb, t->attb, Rpad, D, BM));
   TRY(make_tmap(&t->tm_ffb, t->ffb, Rpad, F, BM));
-  TRY(make_tmap(&t->tm_Wxp, t->Wxp, D, Jpad, 256));
+  TRY(make_tmap(&t->tm_Wxp, t->Wxp, D, Jpad, bn_d));
   TRY(make_tmap(&t->tm_Wout, t->Wout, Jpad, D, 128));
   CUDA_TRY(cudaStreamCreateWithFlags(&t->main, cudaStreamNonBlocking));
   CUDA_TRY(cudaStreamCreateWithFlags(&t->side, cudaStreamNonBlocking));
@@ -205,7 +210,7 @@ static int tc_pack_x(dsg_engine* e, int B, const float* x, cudaStream_t st) {
 }
 
 static int tc_noise(dsg_engine* e, int B, StepRef step, cudaStream_t st) {
-  NoiseArgs a{e->tc->z, e->clip_ids, step, B, (long long)e->d.njoints * e->d.n_poses, e->sampler};
+  NoiseArgs a{e->tc->z, e->noise_ids, step, B, (long long)e->d.njoints * e->d.n_poses, e->sampler};
   noise_tile_kernel<<<elementwise_grid(e, (a.per_clip >> 2) * B), 256, 0, st>>>(a);
   e->launches++;
   CUDA_TRY(cudaGetLastError());
@@ -225,12 +230,38 @@ static int tc_attention(dsg_engine* e, int B, cudaStream_t st) {
   dsg_tc_state* t = e->tc;
   static const bool simt = getenv("DSG_ATTN") && !strcmp(getenv("DSG_ATTN"), "simt");
   const int hd = e->d.latent_dim / e->d.num_heads;
-  if (simt || hd != 64 || e->S > 96) return launch_self_attention_bf16(e, B, t->qkvb, t->attb, st);
   const float scale_log2e = 1.4426950408889634f / sqrtf((float)hd);
-  self_attention_mma_kernel<6><<<B * e->d.num_heads, 192, 0, st>>>(t->qkvb, t->attb, e->S, e->d.latent_dim, e->d.num_heads, scale_log2e);
+  const int grid = B * e->d.num_heads;
+  bool done = false;
+#define ATTN_CASE(RT, HD)                                                                                                  \
+  if (!done && !simt && hd == HD && e->S <= 16 * RT) {                                                                      \
+    constexpr int smem = 3 * 16 * RT * (HD + 8) * 2;                                                                        \
+    static bool configured = false;                                                                                         \
+    if (!configured) {                                                                                                      \
+      CUDA_TRY(cudaFuncSetAttribute(self_attention_mma_kernel<RT, HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+      configured = true;                                                                                                    \
+    }                                                                                                                       \
+    self_attention_mma_kernel<RT, HD><<<grid, 32 * RT, smem, st>>>(t->qkvb, t->attb, e->S, e->d.latent_dim, e->d.num_heads, scale_log2e); \
+    done = true;                                                                                                            \
+  }
+  ATTN_CASE(6, 64)        // ZEGGS: S = 89, 4 x 64
+  ATTN_CASE(10, 96)       // BEAT "+": S = 151, 4 x 96
+  ATTN_CASE(10, 128)      // TWH "+":  S = 151, 4 x 128
+#undef ATTN_CASE
+  if (!done) return launch_self_attention_bf16(e, B, t->qkvb, t->attb, st);      // any other geometry: CUDA-core kernel
   e->launches++;
   CUDA_TRY(cudaGetLastError());
   return DSG_OK;
+}
+
+// out_proj / linear2 + residual + LayerNorm: one D-wide tile per 128 rows (the whole row's statistics live in one accumulator)
+static int launch_ln(dsg_engine* e, const CUtensorMap& a, const CUtensorMap& w, const TcEpiArgs& ep, cudaStream_t st) {
+  switch (e->d.latent_dim) {
+    case 256: return launch_tc<256, 4, EPI_LN>(e, a, w, ep, 1, st);
+    case 384: return launch_tc<384, 3, EPI_LN>(e, a, w, ep, 1, st);
+    case 512: return launch_tc<512, 2, EPI_LN>(e, a, w, ep, 1, st);
+  }
+  return dsg_fail(DSG_ERR_UNSUPPORTED, "LayerNorm GEMM: latent_dim %d", e->d.latent_dim);
 }
 
 // everything of one denoiser call up to (not including) the head GEMM
@@ -244,7 +275,8 @@ static int tc_body(dsg_engine* e, int B, const int* tsel, StepRef step, cudaStre
   {  // h = Wxp x_t + cond + TW[t]
     TcEpiArgs a = ep;
     a.N = D; a.K = t->Jpad; a.out = t->hS; a.cond = e->cond; a.TW = e->TW; a.tsel = tsel; a.tmap = e->tmap;
-    PROF(e, PT_GEMM_IN, st, (launch_tc<256, 4, EPI_IN>(e, t->tm_xb, t->tm_Wxp, a, 1, st)));
+    if (t->bn_d == 256) PROF(e, PT_GEMM_IN, st, (launch_tc<256, 4, EPI_IN>(e, t->tm_xb, t->tm_Wxp, a, D / 256, st)));
+    else PROF(e, PT_GEMM_IN, st, (launch_tc<128, 4, EPI_IN>(e, t->tm_xb, t->tm_Wxp, a, D / 128, st)));
   }
   PROF(e, PT_LOCAL_ATTN, st, launch_local_attention(e, B, t->hS, (long long)S * D, 1, e->xs, t->xsb, tsel, step, st));
   TRY(tc_debug_snap(e, 0, B, st));
@@ -253,13 +285,14 @@ static int tc_body(dsg_engine* e, int B, const int* tsel, StepRef step, cudaStre
     {
       TcEpiArgs a = ep;
       a.N = 3 * D; a.K = D; a.bias = w[L_INPROJ_B]; a.out = t->qkvb; a.ldc = 3 * D;
-      PROF(e, PT_GEMM_QKV, st, (launch_tc<256, 4, EPI_BF16>(e, t->tm_xsb, t->tm_Wqkv[l], a, 3 * D / 256, st)));
+      if (t->bn_d == 256) PROF(e, PT_GEMM_QKV, st, (launch_tc<256, 4, EPI_BF16>(e, t->tm_xsb, t->tm_Wqkv[l], a, 3 * D / 256, st)));
+      else PROF(e, PT_GEMM_QKV, st, (launch_tc<128, 4, EPI_BF16>(e, t->tm_xsb, t->tm_Wqkv[l], a, 3 * D / 128, st)));
     }
     PROF(e, PT_SELF_ATTN, st, tc_attention(e, B, st));
     {
       TcEpiArgs a = ep;
       a.N = D; a.K = D; a.bias = w[L_OUTPROJ_B]; a.xs = e->xs; a.xsb = t->xsb; a.gamma = w[L_N1_W]; a.beta = w[L_N1_B];
-      PROF(e, PT_GEMM_OUTPROJ, st, (launch_tc<256, 4, EPI_LN>(e, t->tm_attb, t->tm_Wo[l], a, 1, st)));
+      PROF(e, PT_GEMM_OUTPROJ, st, launch_ln(e, t->tm_attb, t->tm_Wo[l], a, st));
     }
     {
       TcEpiArgs a = ep;
@@ -269,7 +302,7 @@ static int tc_body(dsg_engine* e, int B, const int* tsel, StepRef step, cudaStre
     {
       TcEpiArgs a = ep;
       a.N = D; a.K = F; a.bias = w[L_FF2_B]; a.xs = e->xs; a.xsb = t->xsb; a.gamma = w[L_N2_W]; a.beta = w[L_N2_B];
-      PROF(e, PT_GEMM_FF2, st, (launch_tc<256, 4, EPI_LN>(e, t->tm_ffb, t->tm_W2[l], a, 1, st)));
+      PROF(e, PT_GEMM_FF2, st, launch_ln(e, t->tm_ffb, t->tm_W2[l], a, st));
     }
     TRY(tc_debug_snap(e, l + 1, B, st));
   }
@@ -331,14 +364,14 @@ static int tc_capture(dsg_engine* e, int B) {
   return DSG_OK;
 }
 
-int dsg_tc_run_steps(dsg_engine* e, int B, float* xd, int n_run, int first_index, uint64_t seed, int segment, cudaStream_t st) {
+int dsg_tc_run_steps(dsg_engine* e, int B, float* xd, int k0, int n_run, int first_index, uint64_t seed, int segment, cudaStream_t st) {
   dsg_tc_state* t = e->tc;
   // DSG_TC_MODE=kernels selects the multi-kernel graph path (default: the persistent clip kernel when the geometry allows)
   const bool force_kernels = getenv("DSG_TC_MODE") && !strcmp(getenv("DSG_TC_MODE"), "kernels");
-  if (t->clip_ok && !force_kernels && !e->profiling) return clip_run(e, B, xd, n_run, first_index, seed, segment, st);
+  if (t->clip_ok && !force_kernels && !e->profiling) return clip_run(e, B, xd, k0, n_run, first_index, seed, segment, st);
   if (e->profiling || e->debug) {
     TRY(tc_pack_x(e, B, xd, st));
-    for (int k = 0; k < n_run; ++k) {
+    for (int k = k0; k < k0 + n_run; ++k) {
       const StepRef step{nullptr, k, first_index, (uint32_t)(seed & 0xffffffffu), (uint32_t)(seed >> 32), (uint32_t)segment};
       TRY(tc_body(e, B, nullptr, step, st));
       PROF(e, PT_NOISE, st, tc_noise(e, B, step, st));
@@ -352,7 +385,7 @@ int dsg_tc_run_steps(dsg_engine* e, int B, float* xd, int n_run, int first_index
   // the graph works on an engine-owned copy of x, so one instantiation serves every segment / caller buffer
   const size_t xbytes = (size_t)B * e->d.njoints * e->d.n_poses * sizeof(float);
   CUDA_TRY(cudaMemcpyAsync(t->xloop, xd, xbytes, cudaMemcpyDeviceToDevice, t->main));
-  TRY(dsg_upload_loop_params(e, first_index, seed, segment, t->main));
+  TRY(dsg_upload_loop_params(e, k0, first_index, seed, segment, t->main));
   TRY(tc_pack_x(e, B, t->xloop, t->main));
   int k_start = 0;
   if (!e->graph_valid || !t->exec || t->graph_B != B || t->graph_sampler != e->sampler) {

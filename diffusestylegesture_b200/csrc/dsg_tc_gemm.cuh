@@ -144,6 +144,14 @@ DSG_DEVINL constexpr uint32_t make_idesc_f16(int m, int n) {
   return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
+// BN <= 256: one UMMA per k-step.  BN = 384 / 512 (a full LayerNorm row of the "+" denoisers, D = 384 / 512): the B tile is
+// two TMA boxes of BN/2 rows and every k-step issues two UMMAs of N = BN/2 into adjacent TMEM column ranges.
+template <int BN> struct TcTile {
+  static constexpr int NSPLIT = BN > 256 ? 2 : 1;
+  static constexpr int NSUB = BN / NSPLIT;                                   // UMMA N and TMA box rows of the B operand
+  static constexpr int TMEM_COLS = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : (BN <= 256 ? 256 : 512)));
+  static_assert(NSUB % 16 == 0 && NSUB <= 256 && BN <= 512, "UMMA N: multiple of 16, <= 256 (M = 128)");
+};
 template <int BN, int STAGES>
 struct TcSmem {
   static constexpr int A_BYTES = BM * BK * 2;
@@ -223,13 +231,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)BN) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)TcTile<BN>::TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  constexpr int NSPLIT = TcTile<BN>::NSPLIT, NSUB = TcTile<BN>::NSUB;
 
   if (warp == 0 && lane == 0) {
     // ===== TMA producer =====
@@ -241,11 +250,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       uint8_t* a_dst = smem + s * SM::STAGE_BYTES;
       if (ep.rows_per_z > 0) tma_load_3d(a_dst, &tmA, &full_bar[s], kb * BK, m0, (int)blockIdx.z);
       else tma_load_2d(a_dst, &tmA, &full_bar[s], kb * BK, m0);
-      tma_load_2d(a_dst + SM::A_BYTES, &tmB, &full_bar[s], kb * BK, n0);
+#pragma unroll
+      for (int i = 0; i < NSPLIT; ++i)
+        tma_load_2d(a_dst + SM::A_BYTES + i * NSUB * 128, &tmB, &full_bar[s], kb * BK, n0 + i * NSUB);
     }
   } else if (warp == 1 && lane == 0) {
     // ===== MMA issuer =====
-    constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
+    constexpr uint32_t idesc = make_idesc_bf16(BM, NSUB);
     for (int kb = 0; kb < num_kb; ++kb) {
       const int s = kb % STAGES;
       const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
@@ -256,8 +267,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
       for (int k = 0; k < BK / UMMA_K; ++k) {
         const uint64_t adesc = make_sw128_desc(a_addr + k * UMMA_K * 2);
-        const uint64_t bdesc = make_sw128_desc(b_addr + k * UMMA_K * 2);
-        umma_bf16(tmem_base, adesc, bdesc, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+        for (int i = 0; i < NSPLIT; ++i)
+          umma_bf16(tmem_base + i * NSUB, adesc, make_sw128_desc(b_addr + i * NSUB * 128 + k * UMMA_K * 2), idesc, (kb > 0 || k > 0) ? 1u : 0u);
       }
       tcgen05_commit(&empty_bar[s]);            // frees the smem stage when these MMAs retire
     }
@@ -444,7 +456,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   if (warp == 2) {
     tcgen05_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TcTile<BN>::TMEM_COLS) : "memory");
   }
 }
 

@@ -68,7 +68,7 @@ static __global__ void bump_step_kernel(LoopParams* lp) { lp->k += 1; }
 // Global self-attention on tensor cores (nn.TransformerEncoderLayer's SDPA: softmax(q k^T / sqrt(hd)) v, no mask;
 // mdm.py:79-86).  One CTA per (clip, head), warp w owns query rows 16w..16w+15; S <= 16*RT keys, head dim 64.
 // The problem per CTA is 96 x 96 x 64 — far below a tcgen05 tile (128 x N), so this uses the warp-level
-// mma.sync.m16n8k16 bf16 path (HMMA): Q K^T accumulators stay in registers, are soft-maxed in place and re-used
+// mma.sync.m16n8k16 bf16 path (HMMA; dynamic shared memory = 3 * 16 RT * (HD + 8) * 2 bytes): Q K^T accumulators stay in registers, are soft-maxed in place and re-used
 // as the A fragments of P V (FlashAttention-2 register layout); K/V/Q tiles are staged once in shared memory
 // with a 16-byte row pad so that every ldmatrix is bank-conflict free.
 // qkv: bf16 [B*S, 3D] (q | k | v), out: bf16 [B*S, D].
@@ -91,14 +91,15 @@ DSG_DEVINL uint32_t pack_bf16x2(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&p);
 }
 
-template <int RT>   // row tiles of 16: S <= 16 * RT
+template <int RT, int HD>   // row tiles of 16: S <= 16 * RT; head dim HD (64: ZEGGS, 96 / 128: the "+" denoisers with S = 151)
 __global__ void __launch_bounds__(32 * RT) self_attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv,
                                                                     __nv_bfloat16* __restrict__ out, int S, int D, int heads,
                                                                     float scale_log2e) {
-  constexpr int HD = 64, LDS = HD + 8, ROWS = 16 * RT;
-  __shared__ __align__(16) __nv_bfloat16 Qs[ROWS][LDS];
-  __shared__ __align__(16) __nv_bfloat16 Ks[ROWS][LDS];
-  __shared__ __align__(16) __nv_bfloat16 Vs[ROWS][LDS];
+  constexpr int LDS = HD + 8, ROWS = 16 * RT;
+  extern __shared__ __align__(16) uint8_t attn_smem[];
+  __nv_bfloat16 (*Qs)[LDS] = reinterpret_cast<__nv_bfloat16 (*)[LDS]>(attn_smem);
+  __nv_bfloat16 (*Ks)[LDS] = Qs + ROWS;
+  __nv_bfloat16 (*Vs)[LDS] = Ks + ROWS;
   const int clip = blockIdx.x / heads, head = blockIdx.x - clip * heads;
   const __nv_bfloat16* base = qkv + (long long)clip * S * 3 * D + head * HD;
   for (int e = threadIdx.x; e < ROWS * 3 * (HD / 8); e += blockDim.x) {

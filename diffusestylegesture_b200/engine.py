@@ -15,10 +15,11 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdsg.so")
 
 PRECISION = {"fp32": 0, "bf16": 1}
-SAMPLER = {"ddpm": 0, "ddim": 1}
+SAMPLER = {"ddpm": 0, "ddim": 1, "plms": 2}
+LOOP_CONST_NOISE = 1
 
 EXPORTS = ["dsg_engine_create", "dsg_engine_destroy", "dsg_set_schedule", "dsg_set_conditioning", "dsg_denoise",
-           "dsg_posterior_step", "dsg_sample_loop", "dsg_stitch_segment", "dsg_kernel_launch_count",
+           "dsg_posterior_step", "dsg_sample_loop", "dsg_sample_loop_ex", "dsg_set_conditioning_ex", "dsg_stitch_segment", "dsg_kernel_launch_count",
            "dsg_debug_read", "dsg_profile", "dsg_profile_read", "dsg_profile_tag_name", "dsg_selftest_gemm", "dsg_wavlm_create", "dsg_wavlm_forward", "dsg_wavlm_frames",
            "dsg_wavlm_launch_count", "dsg_wavlm_destroy", "dsg_last_error", "dsg_version"]
 
@@ -28,6 +29,11 @@ class _Desc(ctypes.Structure):
         "variant", "njoints", "n_poses", "n_seed", "latent_dim", "ff_size", "num_layers", "num_heads", "local_heads",
         "local_window", "audio_dim", "audio_latent", "style_in", "style_latent", "num_timesteps", "max_batch",
         "precision", "device")]
+
+
+class _LoopOpts(ctypes.Structure):
+    _fields_ = [("flags", ctypes.c_int32), ("plms_order", ctypes.c_int32), ("n_dump", ctypes.c_int32),
+                ("dump_iters", ctypes.c_void_p), ("dump_out", ctypes.c_void_p)]
 
 
 _lib = None
@@ -53,9 +59,11 @@ def load_library(path=None):
     lib.dsg_denoise.argtypes = [vp, i32, vp, vp, vp, vp]
     lib.dsg_posterior_step.argtypes = [vp, i32, vp, vp, i32, u64, vp, i32, i32, vp]
     lib.dsg_sample_loop.argtypes = [vp, i32, vp, i32, u64, vp, i32, i32, vp, vp]
+    lib.dsg_sample_loop_ex.argtypes = [vp, i32, vp, i32, u64, vp, i32, i32, vp, ctypes.POINTER(_LoopOpts), vp]
+    lib.dsg_set_conditioning_ex.argtypes = [vp, i32, vp, vp, vp, vp, vp]
     lib.dsg_stitch_segment.argtypes = [vp, i32, vp, vp, i32, vp]
     for f in ("dsg_set_schedule", "dsg_set_conditioning", "dsg_denoise", "dsg_posterior_step", "dsg_sample_loop",
-              "dsg_stitch_segment"):
+              "dsg_sample_loop_ex", "dsg_set_conditioning_ex", "dsg_stitch_segment"):
         getattr(lib, f).restype = ctypes.c_int
     lib.dsg_kernel_launch_count.argtypes = [vp]
     lib.dsg_kernel_launch_count.restype = i64
@@ -164,14 +172,17 @@ class Engine:
         self._sched_key = key
 
     # -- conditioning / denoiser ---------------------------------------------------------------------
-    def set_conditioning(self, style, seed, audio):
+    def set_conditioning(self, style, seed, audio, seed_last=None):
         g = self.g
         B = style.shape[0]
         style = self._f32(style).reshape(B, g.style_in)
         seed = self._f32(seed).reshape(B, g.njoints, 1, g.n_seed)
         audio = self._f32(audio).reshape(B, g.audio_frames, g.audio_dim)
-        _check(self.lib, self.lib.dsg_set_conditioning(self.h, B, _ptr(style), _ptr(seed), _ptr(audio), _stream(self.device)))
-        self._keep = (style, seed, audio)      # keep staged host sources alive until the stream consumed them
+        if seed_last is not None:              # the "++" variant (BEAT-TWH-main/model/mdm.py:229)
+            seed_last = self._f32(seed_last).expand(B, g.njoints, 1, g.n_seed).contiguous()
+        _check(self.lib, self.lib.dsg_set_conditioning_ex(self.h, B, _ptr(style), _ptr(seed), _ptr(audio), _ptr(seed_last),
+                                                          _stream(self.device)))
+        self._keep = (style, seed, audio, seed_last)      # keep staged host sources alive until the stream consumed them
 
     def denoise(self, x, timesteps, out=None):
         B = x.shape[0]
@@ -190,12 +201,25 @@ class Engine:
                                                      _ptr(ids), int(segment), int(draw), _stream(self.device)))
         return x
 
-    def sample_loop(self, x, noise_given, seed, clip_ids=None, segment=0, skip_timesteps=0, init_image=None):
+    def sample_loop(self, x, noise_given, seed, clip_ids=None, segment=0, skip_timesteps=0, init_image=None,
+                    const_noise=False, dump_steps=None, plms_order=0):
+        """dsg_sample_loop_ex.  Returns x (final sample, in place), or the list of dumped samples when ``dump_steps`` is
+        given (gaussian_diffusion.py:647-669: the loop then returns ``dump``, not the final sample)."""
         B = x.shape[0]
         ids = None if clip_ids is None else np.ascontiguousarray(clip_ids, dtype=np.int64)
         init = None if init_image is None else self._f32(init_image)
-        _check(self.lib, self.lib.dsg_sample_loop(self.h, B, _ptr(x), int(bool(noise_given)), int(seed), _ptr(ids),
-                                                  int(segment), int(skip_timesteps), _ptr(init), _stream(self.device)))
+        opts = _LoopOpts(LOOP_CONST_NOISE if const_noise else 0, int(plms_order), 0, None, None)
+        iters = dump = None
+        if dump_steps is not None:
+            n_run = None
+            iters = np.ascontiguousarray(sorted(set(int(i) for i in dump_steps if int(i) >= 0)), dtype=np.int32)
+            dump = torch.empty((len(iters),) + tuple(x.shape), dtype=torch.float32, device=x.device)
+            opts.n_dump, opts.dump_iters, opts.dump_out = len(iters), iters.ctypes.data, dump.data_ptr()
+        _check(self.lib, self.lib.dsg_sample_loop_ex(self.h, B, _ptr(x), int(bool(noise_given)), int(seed), _ptr(ids),
+                                                     int(segment), int(skip_timesteps), _ptr(init), ctypes.byref(opts),
+                                                     _stream(self.device)))
+        if dump_steps is not None:
+            return [dump[i] for i in range(len(iters))]
         return x
 
     def stitch_segment(self, prev_tail, sample, smoothing=True):

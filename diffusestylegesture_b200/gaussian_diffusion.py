@@ -4,8 +4,9 @@ main/diffusion/respace.py): same class names, constructor arguments, table attri
 (one C call per segment: ``dsg_sample_loop``, include/dsg.h) instead of ~150 ATen launches per step.
 
 Only what the sampling path needs is here: schedule tables (float64, host, once), option checking
-and the hand-off to the engine.  Training losses, PLMS, learned-variance models and guidance hooks are
-outside the hot path; the corresponding arguments raise ``NotImplementedError`` (no silent fallback).
+and the hand-off to the engine: ``p_sample_loop`` (with ``const_noise`` / ``dump_steps``), ``ddim_sample_loop``
+(eta = 0) and ``plms_sample_loop`` (order 2..4).  Training losses, learned-variance models and guidance hooks
+are outside the hot path; the corresponding arguments raise ``NotImplementedError`` (no silent fallback).
 """
 import enum
 import math
@@ -112,7 +113,8 @@ class GaussianDiffusion:
         return coef, qs, np.asarray(self.timestep_map, dtype=np.int32)
 
     # ---- the loop ----
-    def _run(self, sampler, model, shape, noise, model_kwargs, skip_timesteps, init_image, device):
+    def _run(self, sampler, model, shape, noise, model_kwargs, skip_timesteps, init_image, device, const_noise=False,
+             dump_steps=None, order=0):
         if self.model_mean_type != ModelMeanType.START_X:
             raise NotImplementedError("only ModelMeanType.START_X (the reference always predicts x_start)")
         if not isinstance(shape, (tuple, list)):
@@ -128,7 +130,7 @@ class GaussianDiffusion:
         model.check_mask_local(y)
         coef, qs, tmap = self.engine_tables(sampler)
         engine.set_schedule(sampler, coef, qs, tmap)
-        engine.set_conditioning(y["style"], y["seed"], y["audio"])
+        engine.set_conditioning(y["style"], y["seed"], y["audio"], y.get("seed_last", None))
         if noise is not None:
             x = noise.detach().to(device=engine.device, dtype=torch.float32).clone().contiguous()
             assert tuple(x.shape) == tuple(shape)
@@ -139,24 +141,47 @@ class GaussianDiffusion:
         if segment is None:          # successive calls must not reuse x_T (the reference's RNG state advances)
             segment = self._calls
         self._calls += 1
-        engine.sample_loop(x, noise is not None, seed, clip_ids=y.get("clip_ids", None), segment=int(segment),
-                           skip_timesteps=int(skip_timesteps), init_image=init_image)
-        return x
+        if dump_steps is not None:
+            n_run = self.num_timesteps - int(skip_timesteps)
+            dump_steps = [int(i) for i in dump_steps if 0 <= int(i) < n_run]      # `if i in dump_steps` (:664): others never match
+        return engine.sample_loop(x, noise is not None, seed, clip_ids=y.get("clip_ids", None), segment=int(segment),
+                                  skip_timesteps=int(skip_timesteps), init_image=init_image, const_noise=bool(const_noise),
+                                  dump_steps=dump_steps, plms_order=int(order))
 
     def p_sample_loop(self, model, shape, noise=None, clip_denoised=True, denoised_fn=None, cond_fn=None,
                       model_kwargs=None, device=None, progress=False, skip_timesteps=0, init_image=None,
                       randomize_class=False, cond_fn_with_grad=False, dump_steps=None, const_noise=False):
-        """gaussian_diffusion.py:608-671 — same signature; returns the final sample [B, J, 1, T] on the GPU."""
+        """gaussian_diffusion.py:608-671 — same signature; returns the final sample [B, J, 1, T] on the GPU, or — as the
+        reference does when ``dump_steps`` is given (:647-669) — the list of samples after those loop iterations.
+        ``const_noise`` (:544-545): every clip is noised with clip 0's per-step noise."""
         _reject(clip_denoised=(clip_denoised, False), denoised_fn=(denoised_fn, None), cond_fn=(cond_fn, None),
-                randomize_class=(randomize_class, False), cond_fn_with_grad=(cond_fn_with_grad, False),
-                dump_steps=(dump_steps, None), const_noise=(const_noise, False))
-        return self._run("ddpm", model, shape, noise, model_kwargs, skip_timesteps, init_image, device)
+                randomize_class=(randomize_class, False), cond_fn_with_grad=(cond_fn_with_grad, False))
+        return self._run("ddpm", model, shape, noise, model_kwargs, skip_timesteps, init_image, device,
+                         const_noise=const_noise, dump_steps=dump_steps)
+
+    def plms_sample_loop(self, model, shape, noise=None, clip_denoised=True, denoised_fn=None, cond_fn=None,
+                         model_kwargs=None, device=None, progress=False, skip_timesteps=0, init_image=None,
+                         randomize_class=False, cond_fn_with_grad=False, order=2):
+        """gaussian_diffusion.py:1105-1134 — Pseudo Linear Multistep sampling (deterministic; eps re-derived from the
+        predicted x_start, :1049).  order 2..4: order 1 dereferences ``old_out=None`` on the first step in the reference."""
+        _reject(clip_denoised=(clip_denoised, False), denoised_fn=(denoised_fn, None), cond_fn=(cond_fn, None),
+                randomize_class=(randomize_class, False), cond_fn_with_grad=(cond_fn_with_grad, False))
+        if not int(order) or not 1 <= order <= 4:
+            raise ValueError('order is invalid (should be int from 1-4).')           # :1023-1024
+        if int(order) == 1:
+            raise TypeError("order=1: the reference fails on its first step ('NoneType' object is not subscriptable, "
+                            "gaussian_diffusion.py:1069)")
+        return self._run("plms", model, shape, noise, model_kwargs, skip_timesteps, init_image, device, order=int(order))
 
     def ddim_sample_loop(self, model, shape, noise=None, clip_denoised=True, denoised_fn=None, cond_fn=None,
                          model_kwargs=None, device=None, progress=False, eta=0.0, skip_timesteps=0, init_image=None,
                          randomize_class=False, cond_fn_with_grad=False, dump_steps=None, const_noise=False):
-        """gaussian_diffusion.py:889-935 — eta = 0 only (deterministic DDIM)."""
+        """gaussian_diffusion.py:889-935 — eta = 0 only (deterministic DDIM).  ``dump_steps`` / ``const_noise`` raise
+        NotImplementedError exactly as in the reference (:913-916)."""
+        if dump_steps is not None:
+            raise NotImplementedError()
+        if const_noise:
+            raise NotImplementedError()
         _reject(clip_denoised=(clip_denoised, False), denoised_fn=(denoised_fn, None), cond_fn=(cond_fn, None),
-                randomize_class=(randomize_class, False), cond_fn_with_grad=(cond_fn_with_grad, False),
-                dump_steps=(dump_steps, None), const_noise=(const_noise, False), eta=(eta, 0.0))
+                randomize_class=(randomize_class, False), cond_fn_with_grad=(cond_fn_with_grad, False), eta=(eta, 0.0))
         return self._run("ddim", model, shape, noise, model_kwargs, skip_timesteps, init_image, device)

@@ -6,7 +6,7 @@ keep working — but it holds parameters only.  ``forward`` and the sampling loo
 import torch
 from torch import nn
 
-from .config import ModelGeometry, state_dict_spec, VARIANT_ZEGGS_ATTN3, VARIANT_BEAT_ATTN4
+from .config import ModelGeometry, state_dict_spec, VARIANT_ZEGGS_ATTN3, VARIANT_BEAT_ATTN4, VARIANT_BEAT_ATTN5
 from .engine import Engine
 from .synthetic import synthetic_state_dict
 
@@ -39,8 +39,13 @@ class MDM(nn.Module):
                               latent_dim=latent_dim, ff_size=ff_size, num_layers=num_layers, num_heads=num_heads,
                               local_window=15, audio_dim=source_audio_dim, audio_latent=audio_feat_dim_latent,
                               style_in=style_dim, style_latent=latent_dim)
+        elif 'cross_local_attention5' in cond_mode and 'style1' in cond_mode:
+            g = ModelGeometry(variant=VARIANT_BEAT_ATTN5, njoints=njoints, n_poses=n_poses or 150, n_seed=n_seed,
+                              latent_dim=latent_dim, ff_size=ff_size, num_layers=num_layers, num_heads=num_heads,
+                              local_window=15, audio_dim=source_audio_dim, audio_latent=audio_feat_dim_latent,
+                              style_in=style_dim, style_latent=latent_dim)
         else:
-            raise NotImplementedError(f"cond_mode={cond_mode!r}: cross_local_attention3/4 + style1 are implemented")
+            raise NotImplementedError(f"cond_mode={cond_mode!r}: cross_local_attention3/4/5 + style1 are implemented")
         self.geometry = g
         self.njoints, self.nfeats, self.latent_dim, self.n_seed = njoints, nfeats, latent_dim, n_seed
         self.cond_mode, self.audio_feat, self.arch = cond_mode, audio_feat, arch
@@ -106,6 +111,6 @@ class MDM(nn.Module):
             raise ValueError("y is required")
         self.check_mask_local(y)
         eng = self.get_engine(x.shape[0])
-        eng.set_conditioning(y['style'], y['seed'], y['audio'])
+        eng.set_conditioning(y['style'], y['seed'], y['audio'], y.get('seed_last', None))
         xin = x.detach().to(device=eng.device, dtype=torch.float32).contiguous()
         return eng.denoise(xin, timesteps)

@@ -107,13 +107,17 @@ def segment_plan(n_frames, n_poses, n_seed):
 
 @torch.no_grad()
 def inference_batch(model, diffusion, features, styles, *, seed=123456, clip_ids=None, smoothing=True,
-                    skip_timesteps=0, sampler='ddpm', device=None, out_device='cpu', out=None):
+                    skip_timesteps=0, sampler='ddpm', device=None, out_device='cpu', out=None, seed_pose0=None,
+                    seed_last=None, keep_last_tail=False):
     """B clips x S segments through the engine.
 
     features: sequence (len = segments) of [B, audio_frames, audio_dim] tensors (host or device);  styles: [B, style_in].
     Returns the normalised motion [B, n_frames - n_seed, J] float32 (sample.py:291-296) on ``out_device`` — or in ``out``
     (e.g. a pinned host tensor of that shape: one asynchronous copy instead of a pageable one).
     Host feature tensors in pinned memory are copied one segment ahead on a side stream, under the previous segment's loop.
+    ``seed_pose0`` [B, J, 1, n_seed]: seed of the first segment (default zeros, sample.py:244; the BEAT-TWH driver passes
+    the velocity/acceleration seed of a recorded gesture).  ``seed_last``: y['seed_last'] of the "++" variant.
+    ``keep_last_tail``: the BEAT-TWH driver keeps the last segment's final n_seed frames (its sample.py:189-199).
     """
     g = model.geometry
     nseg = len(features) if not callable(features) else None
@@ -129,7 +133,10 @@ def inference_batch(model, diffusion, features, styles, *, seed=123456, clip_ids
         sample_fn = getattr(diffusion, sample_fn)
     styles = torch.as_tensor(styles, dtype=torch.float32)
     shape_ = (B, g.njoints, 1, g.n_poses)
-    seed_pose = torch.zeros(B, g.njoints, 1, g.n_seed, device=dev)              # sample.py:244
+    if seed_pose0 is None:
+        seed_pose = torch.zeros(B, g.njoints, 1, g.n_seed, device=dev)          # sample.py:244
+    else:
+        seed_pose = torch.as_tensor(seed_pose0, dtype=torch.float32).to(dev).expand(B, g.njoints, 1, g.n_seed).contiguous()
     pieces, prev = [], None
     main = torch.cuda.current_stream(dev)
     side = torch.cuda.Stream(dev) if any((not f.is_cuda) and f.is_pinned() for f in features) else None
@@ -148,6 +155,8 @@ def inference_batch(model, diffusion, features, styles, *, seed=123456, clip_ids
         y = {'style': styles, 'seed': seed_pose, 'audio': cur,
              'mask_local': torch.ones(1, g.n_poses, dtype=torch.bool),
              'noise_seed': seed, 'segment': i, 'clip_ids': clip_ids}
+        if seed_last is not None:
+            y['seed_last'] = seed_last
         sample = sample_fn(model, shape_, clip_denoised=False, model_kwargs={'y': y}, skip_timesteps=skip_timesteps,
                            init_image=None, progress=False, dump_steps=None, noise=None, const_noise=False)
         if isinstance(cur, torch.Tensor) and cur.is_cuda:
@@ -161,7 +170,7 @@ def inference_batch(model, diffusion, features, styles, *, seed=123456, clip_ids
             pieces.append(prev)
         prev = sample
         seed_pose = sample[..., -g.n_seed:].contiguous()                          # sample.py:249
-    pieces.append(prev[..., :-g.n_seed] if g.n_seed != 0 else prev)               # sample.py:292
+    pieces.append(prev[..., :-g.n_seed] if (g.n_seed != 0 and not keep_last_tail) else prev)        # sample.py:292
     seq = torch.cat(pieces, dim=-1)[:, :, 0, :].transpose(1, 2)                   # [B, n_frames, J]
     seq = seq[:, g.n_seed:] if g.n_seed != 0 else seq                             # sample.py:296
     if out is not None:

@@ -20,7 +20,8 @@
  *     with DSG_ERR_BAD_ARCH.
  *   - Layouts: x / seed are the reference's [B, njoints, 1, frames] fp32 (frames innermost);
  *     audio is [B, audio_frames, audio_dim]; style is [B, style_in].
- *   - An engine is bound to one device and is not thread-safe (one engine per GPU / per rank).
+ *   - An engine is bound to one device and is not thread-safe (one engine per GPU / per rank).  Entry points
+ *     switch to the engine's device for the duration of the call and restore the caller's current device.
  */
 #ifndef DSG_H_
 #define DSG_H_
@@ -45,9 +46,12 @@ typedef enum dsg_status {
 enum { DSG_PRECISION_FP32 = 0,   /* fp32 CUDA-core kernels: the validation path (matches the fp32 reference to ~1e-5) */
        DSG_PRECISION_BF16 = 1 }; /* bf16 operands on tcgen05 tensor cores, fp32 accumulate / residual / LN / posterior  */
 enum { DSG_SAMPLER_DDPM = 0,     /* GaussianDiffusion.p_sample       (gaussian_diffusion.py:506-558)  */
-       DSG_SAMPLER_DDIM = 1 };   /* GaussianDiffusion.ddim_sample, eta = 0 (gaussian_diffusion.py:742-792) */
+       DSG_SAMPLER_DDIM = 1,     /* GaussianDiffusion.ddim_sample, eta = 0 (gaussian_diffusion.py:742-792) */
+       DSG_SAMPLER_PLMS = 2 };   /* GaussianDiffusion.plms_sample, order 2..4 (gaussian_diffusion.py:1005-1103); DDIM coefficient rows */
 enum { DSG_VARIANT_ATTN3 = 3,    /* cond_mode cross_local_attention3_style1 (main/model/mdm.py:194-233)  */
-       DSG_VARIANT_ATTN4 = 4 };  /* cond_mode cross_local_attention4_style1 (BEAT-TWH-main/model/mdm.py:187-224) */
+       DSG_VARIANT_ATTN4 = 4,    /* cond_mode cross_local_attention4_style1 (BEAT-TWH-main/model/mdm.py:187-224) */
+       DSG_VARIANT_ATTN5 = 5 };  /* cond_mode cross_local_attention5_style1 ("++": + seed_last / embed_text_last, :226-264);
+                                    its two extra tensors embed_text_last.{weight,bias} come LAST in the weight list */
 
 /* Geometry of MDM(...) — the constructor arguments of reference main/model/mdm.py:11-151
  * (BEAT-TWH-main/model/mdm.py:11-118 for the "+" variant). */
@@ -109,10 +113,36 @@ int dsg_posterior_step(dsg_engine* e, int32_t batch, float* x, const float* x0, 
  * conditioning last set.  x: [batch, J, 1, T] fp32, in/out.  If noise_given == 0 the engine draws x_T itself
  * (draw 0 of the counter-based stream: Philox4x32-10, key = seed, counter = (element/4, draw, clip, segment));
  * otherwise x holds the caller's `noise`.  init_image (nullable) and skip_timesteps follow :706-713.
- * clip_ids (host, nullable = 0..batch-1) key the noise stream so results do not depend on sharding. */
+ * clip_ids (host, nullable = 0..batch-1; each 0 <= id < 2^32) key the noise stream so results do not depend on sharding. */
 int dsg_sample_loop(dsg_engine* e, int32_t batch, float* x, int32_t noise_given, uint64_t seed,
                     const int64_t* clip_ids, int32_t segment, int32_t skip_timesteps,
                     const float* init_image, void* stream);
+
+/* dsg_sample_loop with the remaining options of the reference loops:
+ *   flags & DSG_LOOP_CONST_NOISE  const_noise=True (gaussian_diffusion.py:544-545): every clip receives clip 0's step noise
+ *                                 (x_T stays per clip: th.randn(*shape), :704);
+ *   dump_iters / dump_out         dump_steps (gaussian_diffusion.py:647-669): a copy of the sample after loop iteration i
+ *                                 (0 = the first, noisiest step) for each listed i, ascending; dump_out is
+ *                                 [n_dump, batch, J, 1, T] fp32, host or device;
+ *   plms_order                    order of plms_sample_loop (DSG_SAMPLER_PLMS schedule only; the reference default is 2,
+ *                                 order 1 fails inside the reference on its first step and is rejected here).
+ * opts == NULL is dsg_sample_loop. */
+enum { DSG_LOOP_CONST_NOISE = 1 };
+typedef struct dsg_loop_opts {
+  int32_t flags;
+  int32_t plms_order;
+  int32_t n_dump;
+  const int32_t* dump_iters;   /* host */
+  float* dump_out;
+} dsg_loop_opts;
+int dsg_sample_loop_ex(dsg_engine* e, int32_t batch, float* x, int32_t noise_given, uint64_t seed,
+                       const int64_t* clip_ids, int32_t segment, int32_t skip_timesteps,
+                       const float* init_image, const dsg_loop_opts* opts, void* stream);
+
+/* dsg_set_conditioning for DSG_VARIANT_ATTN5: seed_last [batch, J, 1, n_seed] is y['seed_last'] (BEAT-TWH-main/model/mdm.py:229);
+ * audio covers n_poses - 2 n_seed frames.  seed_last == NULL is dsg_set_conditioning. */
+int dsg_set_conditioning_ex(dsg_engine* e, int32_t batch, const float* style, const float* seed,
+                            const float* audio, const float* seed_last, void* stream);
 
 /* Batched form of the segment hand-off in inference() (sample.py:266-288): root-position shift and the
  * first-frame 1/2-1/2 blend (the reference's `len(last_poses)` quirk: n == 1 per clip).

@@ -226,6 +226,9 @@ def mdm_forward(W, g, x, t, y, taps=None):
         emb_1 = style
         et = F.linear(seed.permute(0, 2, 1), W["embed_text.weight"], W["embed_text.bias"])   # [B,n_seed,A]
         enc = torch.cat((et, audio), dim=1)                         # [B,T,A]
+        if g.variant == 5:  # "++": BEAT-TWH-main/model/mdm.py:226-230 — audio covers T - 2 n_seed frames
+            last = y["seed_last"].to(dt).squeeze(2)
+            enc = torch.cat((enc, F.linear(last.permute(0, 2, 1), W["embed_text_last.weight"], W["embed_text_last.bias"])), dim=1)
     tok = emb_1 + emb_t                                             # [B,D]
     # InputProcess (mdm.py:461-467) + input_process2 on cat[tok | x_ | enc] (mdm.py:202-206)
     x_ = F.linear(x.squeeze(2).permute(0, 2, 1), W["input_process.poseEmbedding.weight"],
@@ -256,12 +259,14 @@ def mdm_forward(W, g, x, t, y, taps=None):
 # --------------------------------------------------------------------------------------
 def p_sample_loop(W, g, sched, y, batch, *, seed=123456, clip_ids=None, segment=0, sampler="ddpm",
                   skip_timesteps=0, init_image=None, noise=None, dtype=torch.float32,
-                  record_every=0, model_fn=None):
+                  record_every=0, model_fn=None, const_noise=False, dump_steps=None, order=2):
     """Returns (final sample [B,J,1,T], list of (loop_index, x) snapshots).
 
     Draw numbering of the shared noise stream: draw 0 = x_T (``th.randn(*shape)``,
     gaussian_diffusion.py:704); draw 1+k = ``randn_like`` of loop iteration k (:542), k = 0 for the
     first (noisiest) step.  The reference also draws (and discards) noise at t == 0.
+    ``const_noise`` (:544-545): every clip takes clip 0's step noise.  ``dump_steps`` (:647-669): the second return
+    value becomes the list of samples after the listed loop iterations.  ``sampler="plms"``: plms_sample, :1005-1103.
     """
     clip_ids = list(range(batch)) if clip_ids is None else list(clip_ids)
     shp = (g.njoints, 1, g.n_poses)
@@ -279,7 +284,7 @@ def p_sample_loop(W, g, sched, y, batch, *, seed=123456, clip_ids=None, segment=
     for k, i in enumerate(indices):
         t_orig = torch.full((batch,), sched.timestep_map[i], dtype=torch.long)
         x0 = model_fn(img, t_orig)
-        z = noise_tensor(seed, clip_ids, segment, 1 + k, shp).to(dtype)
+        z = noise_tensor(seed, [clip_ids[0]] * batch if const_noise else clip_ids, segment, 1 + k, shp).to(dtype)
         nz = 0.0 if i == 0 else 1.0
         if sampler == "ddpm":      # p_sample + q_posterior_mean_variance, FIXED_SMALL (:264-271, :349-362, :557)
             mean = f(sched.posterior_mean_coef1, i) * x0 + f(sched.posterior_mean_coef2, i) * img
@@ -289,11 +294,73 @@ def p_sample_loop(W, g, sched, y, batch, *, seed=123456, clip_ids=None, segment=
             abar, abar_prev = f(sched.alphas_cumprod, i), f(sched.alphas_cumprod_prev, i)
             sigma = 0.0 * torch.sqrt((1 - abar_prev) / (1 - abar)) * torch.sqrt(1 - abar / abar_prev)
             img = x0 * torch.sqrt(abar_prev) + torch.sqrt(1 - abar_prev - sigma ** 2) * eps + nz * sigma * z
+        elif sampler == "plms":    # plms_sample (:1005-1103): eps history + Adams-Bashforth, pseudo improved Euler first
+            eps_of = lambda xt, x0_, j: (f(sched.sqrt_recip_alphas_cumprod, j) * xt - x0_) / f(sched.sqrt_recipm1_alphas_cumprod, j)
+            sq_prev, sq_1m = torch.sqrt(f(sched.alphas_cumprod_prev, i)), torch.sqrt(1 - f(sched.alphas_cumprod_prev, i))
+            eps = eps_of(img, x0, i)
+            if k == 0:
+                assert order > 1, "order 1 fails inside the reference on the first step (old_out is None, :1069)"
+                old_eps = [eps]
+                mean_pred = x0 * sq_prev + sq_1m * eps
+                x0_2 = model_fn(mean_pred, torch.full((batch,), sched.timestep_map[i - 1], dtype=torch.long))
+                eps_prime = (eps + eps_of(mean_pred, x0_2, i - 1)) / 2
+            else:
+                old_eps.append(eps)
+                cur = min(order, len(old_eps))
+                if cur == 1:
+                    eps_prime = old_eps[-1]
+                elif cur == 2:
+                    eps_prime = (3 * old_eps[-1] - old_eps[-2]) / 2
+                elif cur == 3:
+                    eps_prime = (23 * old_eps[-1] - 16 * old_eps[-2] + 5 * old_eps[-3]) / 12
+                else:
+                    eps_prime = (55 * old_eps[-1] - 59 * old_eps[-2] + 37 * old_eps[-3] - 9 * old_eps[-4]) / 24
+            pred_prime = f(sched.sqrt_recip_alphas_cumprod, i) * img - f(sched.sqrt_recipm1_alphas_cumprod, i) * eps_prime
+            mean_pred = pred_prime * sq_prev + sq_1m * eps_prime
+            if len(old_eps) >= order:
+                old_eps.pop(0)
+            img = mean_pred * nz + x0 * (1 - nz)
         else:
             raise ValueError(sampler)
-        if record_every and (k % record_every == record_every - 1 or k == len(indices) - 1):
+        if dump_steps is not None and k in dump_steps:
+            snaps.append(img.clone())
+        elif dump_steps is None and record_every and (k % record_every == record_every - 1 or k == len(indices) - 1):
             snaps.append((k, img.clone()))
     return img, snaps
+
+
+def inference_clip_beat(W, g, sched, textaudio, style, seed_gesture, *, seed=123456, clip_id=0, skip_timesteps=0,
+                        dtype=torch.float32, seed_last=None, division=3):
+    """BEAT-TWH `inference` (BEAT-TWH-main/mydiffusion_beat_twh/sample.py:44-201) for one clip, "+" / "++" variants.
+    textaudio [n, audio_dim] features; seed_gesture [n_seed, J] = the velocity/acceleration seed of :118-136 (already
+    normalised and concatenated); returns the normalised motion [real_n, J // division] (:176-193, before de-normalising)."""
+    real_n = textaudio.shape[0]
+    stride = g.n_poses - g.n_seed
+    nsub = 1 if real_n < stride else math.ceil(real_n / stride)                      # :56-62
+    n_frames = nsub * stride
+    ta = torch.cat((textaudio.to(dtype), torch.zeros(n_frames - real_n, textaudio.shape[1], dtype=dtype)), 0)     # :71-72
+    audio = ta.reshape(nsub, stride, -1)                                              # :73 (segment-major here)
+    outs = []
+    seed_pose = seed_gesture.to(dtype).T[None, :, None, :]                            # [1,J,1,n_seed]  (:135-136)
+    for i in range(nsub):
+        a = audio[i]
+        if g.variant == 5:
+            a = a[:-g.n_seed]                                                         # :106, :145
+        y = {"audio": a[None], "style": style[None].to(dtype), "seed": seed_pose}
+        if g.variant == 5:
+            y["seed_last"] = seed_last
+        sample, _ = p_sample_loop(W, g, sched, y, 1, seed=seed, clip_ids=[clip_id], segment=i,
+                                  skip_timesteps=skip_timesteps, dtype=dtype)
+        if outs and g.n_seed:                                                         # :163-180 (no root shift in this variant)
+            tail = outs[-1][..., -g.n_seed:]
+            outs[-1] = outs[-1][..., :-g.n_seed]
+            sample = stitch_segment(tail, sample, smoothing=False)
+        outs.append(sample)
+        seed_pose = sample[..., -g.n_seed:]                                           # :147
+    Jd = g.njoints // division
+    # :189-199: all but the last segment were trimmed by n_seed; the last keeps its full length; then drop the first n_seed
+    seq = torch.cat([o[:, :Jd] for o in outs], dim=-1)[0, :, 0, :].T
+    return seq[g.n_seed:][:real_n]
 
 
 # --------------------------------------------------------------------------------------

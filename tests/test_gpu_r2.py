@@ -1,0 +1,215 @@
+"""GPU (B200): round-2 rows — the "+" / "++" denoisers on the tcgen05 path (D = 384 / 512), the remaining sampler options
+(const_noise, dump_steps, PLMS), BASELINE config 3 (B = 64, DDIM-100, six styles) and the BEAT-TWH `inference` driver.
+
+Tolerances (fp32 reference golden, normalised motion |x| <= ~3):
+  fp32 engine                       : loops 2e-3 (as in test_gpu_parity.py)
+  bf16 engine, one denoiser call    : max 0.03 / rms 0.006 (D = 256), max 0.05 / rms 0.008 (D = 384 / 512: K and J are 1.5-2x larger)
+  bf16 engine, loops                : max 0.05 / rms 0.008 (ZEGGS), max 0.08 / rms 0.012 ("+" geometries)
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from diffusestylegesture_b200.config import ZEGGS, BEAT_PLUS, TWH_PLUS, BEAT_PLUSPLUS
+from diffusestylegesture_b200.engine import Engine
+from diffusestylegesture_b200.mdm import MDM
+from diffusestylegesture_b200.model_util import create_gaussian_diffusion, load_model_wo_clip
+from diffusestylegesture_b200.synthetic import synthetic_state_dict, synthetic_conditioning
+from oracle import dsg_oracle as O
+
+pytestmark = pytest.mark.gpu
+SEED = 123456
+G = ZEGGS
+
+
+def _err(a, b):
+    d = (torch.as_tensor(a).double().cpu() - torch.as_tensor(b).double().cpu())
+    return float(d.abs().max()), float(d.pow(2).mean().sqrt())
+
+
+def _zeggs_model(precision, max_batch=2):
+    m = MDM(njoints=G.njoints, cond_mode='cross_local_attention3_style1', audio_feat='wavlm', n_seed=G.n_seed,
+            precision=precision, max_batch=max_batch)
+    load_model_wo_clip(m, synthetic_state_dict(G, seed=0))
+    return m.to('cuda:0').eval()
+
+
+def _plus_model(g, precision, max_batch=2):
+    mode = {4: 'cross_local_attention4_style1_sample', 5: 'cross_local_attention5_style1_sample'}[g.variant]
+    m = MDM(njoints=g.njoints, cond_mode=mode, audio_feat='wavlm', n_seed=g.n_seed, latent_dim=g.latent_dim,
+            style_dim=g.style_in, source_audio_dim=g.audio_dim, audio_feat_dim_latent=g.audio_latent, precision=precision,
+            max_batch=max_batch)
+    load_model_wo_clip(m, synthetic_state_dict(g, seed=0))
+    return m.to('cuda:0').eval()
+
+
+# ------------------------------------------------------------------------------------------------ a18: "+" on tcgen05
+@pytest.mark.parametrize("tag", ["beat", "twh"])
+def test_plus_variant_bf16_tcgen05_vs_reference_golden(gold_dir, tag):
+    """DiffuseStyleGesture+ (D = 384 / 512, T = 150, S = 151, window 15, J = 2052 / 2232) on the tensor-core engine: every
+    Linear a tcgen05 GEMM (LayerNorm GEMMs as one 384- / 512-column tile), attention on mma.sync — against the BEAT-TWH
+    reference golden (BEAT-TWH-main/model/mdm.py:187-224; every 4th channel is stored)."""
+    g = BEAT_PLUS if tag == "beat" else TWH_PLUS
+    gold = np.load(os.path.join(gold_dir, "beat_twh_plus.npz"))
+    sdg = synthetic_state_dict(g, seed=0)
+    e = Engine(g, sdg, device=0, max_batch=2, precision="bf16")
+    y = synthetic_conditioning(g, 2, segment=0)
+    y["seed"] = 0.5 * O.noise_tensor(SEED, [0, 1], 7, 99, (g.njoints, 1, g.n_seed))
+    x = O.noise_tensor(SEED, [0, 1], 0, 0, (g.njoints, 1, g.n_poses))
+    e.set_conditioning(y["style"], y["seed"], y["audio"])
+    l0 = e.launches
+    out = e.denoise(x, gold[f"{tag}/t"])
+    assert e.launches > l0
+    mx, rms = _err(out[:, ::4], gold[f"{tag}/out_sub"])
+    print(f"{tag}+ bf16 denoiser: max {mx:.3g} rms {rms:.3g}")
+    assert mx < 0.05 and rms < 0.008
+    e.close()
+    m = _plus_model(g, "bf16")
+    d = create_gaussian_diffusion([20])
+    yy = dict(y, noise_seed=SEED, segment=0)
+    loop = d.p_sample_loop(m, (2, g.njoints, 1, g.n_poses), clip_denoised=False, model_kwargs={'y': yy})
+    mx, rms = _err(loop[:, ::4], gold[f"{tag}/loop20_sub"])
+    print(f"{tag}+ bf16 ddpm20 loop: max {mx:.3g} rms {rms:.3g}")
+    assert mx < 0.08 and rms < 0.012
+    loop2 = d.p_sample_loop(m, (2, g.njoints, 1, g.n_poses), clip_denoised=False, model_kwargs={'y': yy})
+    assert torch.equal(loop, loop2)                  # graph replay: deterministic
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 3e-4), ("bf16", 0.05)])
+def test_plusplus_attn5_vs_reference_golden(gold_dir, precision, tol):
+    """cross_local_attention5 ("++", BEAT-TWH-main/model/mdm.py:226-264): y['seed_last'] embedded per frame behind the audio."""
+    g = BEAT_PLUSPLUS
+    gold = np.load(os.path.join(gold_dir, "r2_beat.npz"))
+    y = synthetic_conditioning(g, 2, segment=0)
+    y["seed"] = 0.5 * O.noise_tensor(SEED, [0, 1], 7, 99, (g.njoints, 1, g.n_seed))
+    y["seed_last"] = 0.5 * O.noise_tensor(SEED, [0, 1], 7, 98, (g.njoints, 1, g.n_seed))
+    assert np.allclose(y["seed_last"][:, ::4].numpy(), gold["pp/seed_last_sub"])
+    x = O.noise_tensor(SEED, [0, 1], 0, 0, (g.njoints, 1, g.n_poses))
+    m = _plus_model(g, precision)
+    out = m(x, torch.from_numpy(gold["pp/t"]), y=y)
+    mx, rms = _err(out[:, ::4], gold["pp/out_sub"])
+    print(f"beat++ {precision} denoiser: max {mx:.3g} rms {rms:.3g}")
+    assert mx < tol
+    d = create_gaussian_diffusion([20])
+    loop = d.p_sample_loop(m, (2, g.njoints, 1, g.n_poses), clip_denoised=False, model_kwargs={'y': dict(y, noise_seed=SEED, segment=0)})
+    mx, rms = _err(loop[:, ::4], gold["pp/loop20_sub"])
+    print(f"beat++ {precision} ddpm20 loop: max {mx:.3g} rms {rms:.3g}")
+    assert mx < (2e-3 if precision == "fp32" else 0.08)
+    with pytest.raises(RuntimeError, match="seed_last"):
+        m(x, torch.from_numpy(gold["pp/t"]), y={k: v for k, v in y.items() if k != "seed_last"})
+
+
+# ------------------------------------------------------------------------------------------------ f4: sampler options
+@pytest.mark.parametrize("precision,tol", [("fp32", 2e-3), ("bf16", 0.05)])
+def test_const_noise_and_dump_steps_vs_reference_golden(gold_dir, precision, tol):
+    """p_sample_loop(const_noise=True, dump_steps=[0, 10, 49]) (gaussian_diffusion.py:544-545, 647-669): returns the list of
+    dumped samples; every clip is noised with clip 0's per-step noise.  bf16 runs the persistent clip kernel in three launches."""
+    gold = np.load(os.path.join(gold_dir, "r2_zeggs.npz"))
+    m = _zeggs_model(precision)
+    d = create_gaussian_diffusion([50])
+    y = synthetic_conditioning(G, 2, segment=0)
+    y.update(noise_seed=SEED, segment=0)
+    steps = [int(i) for i in gold["opt_dump_steps"]]
+    dump = d.p_sample_loop(m, (2, G.njoints, 1, G.n_poses), clip_denoised=False, model_kwargs={'y': y}, dump_steps=steps,
+                           const_noise=True)
+    assert isinstance(dump, list) and len(dump) == len(steps)
+    for i, (got, want) in enumerate(zip(dump, gold["opt_dump"])):
+        mx, rms = _err(got[:, ::2], want)
+        print(f"{precision} const_noise dump[{steps[i]}]: max {mx:.3g} rms {rms:.3g}")
+        assert mx < tol, (steps[i], mx)
+    # const_noise really changes the result, dump_steps does not: the last dump of a run without const_noise is the plain loop
+    plain = d.p_sample_loop(m, (2, G.njoints, 1, G.n_poses), clip_denoised=False, model_kwargs={'y': y})
+    cut = d.p_sample_loop(m, (2, G.njoints, 1, G.n_poses), clip_denoised=False, model_kwargs={'y': y}, dump_steps=[7, 49])
+    assert torch.equal(cut[-1], plain)
+    assert _err(dump[-1][1], plain[1])[0] > 0.05 and _err(dump[-1][0], plain[0])[0] < 1e-6      # clip 0 keeps its own noise
+    with pytest.raises(NotImplementedError):
+        d.ddim_sample_loop(m, (2, G.njoints, 1, G.n_poses), clip_denoised=False, model_kwargs={'y': y}, dump_steps=[1])
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 3e-3), ("bf16", 0.06)])
+@pytest.mark.parametrize("order", [2, 3])
+def test_plms_sample_loop_vs_reference_golden(gold_dir, precision, tol, order):
+    """plms_sample_loop (gaussian_diffusion.py:1005-1200): pseudo improved Euler first step (two model calls), then
+    Adams-Bashforth of the given order on the eps re-derived from the predicted x_start."""
+    gold = np.load(os.path.join(gold_dir, "r2_zeggs.npz"))
+    m = _zeggs_model(precision)
+    d = create_gaussian_diffusion([50])
+    y = synthetic_conditioning(G, 2, segment=0)
+    y.update(noise_seed=SEED, segment=0)
+    out = d.plms_sample_loop(m, (2, G.njoints, 1, G.n_poses), clip_denoised=False, model_kwargs={'y': y}, order=order)
+    mx, rms = _err(out[:, ::2], gold[f"plms{order}"])
+    print(f"{precision} plms order {order}: max {mx:.3g} rms {rms:.3g}")
+    assert mx < tol
+    with pytest.raises(TypeError):
+        d.plms_sample_loop(m, (2, G.njoints, 1, G.n_poses), clip_denoised=False, model_kwargs={'y': y}, order=1)
+    with pytest.raises(ValueError):
+        d.plms_sample_loop(m, (2, G.njoints, 1, G.n_poses), clip_denoised=False, model_kwargs={'y': y}, order=5)
+
+
+# ------------------------------------------------------------------------------------------------ BASELINE config 3
+def test_config3_b64_ddim100_six_styles_vs_reference_golden(gold_dir):
+    """BASELINE.json configs[2]: batch = 64 ZEGGS clips, style one-hot i mod 6, DDIM-100 (eta 0), clip kernel (bf16) —
+    all 64 clips against the reference's own ddim_sample_loop (every 8th channel stored in fp16, per-clip sums in fp64)."""
+    gold = np.load(os.path.join(gold_dir, "r2_zeggs.npz"))
+    B = 64
+    m = _zeggs_model("bf16", max_batch=B)
+    d = create_gaussian_diffusion("ddim100")
+    y = synthetic_conditioning(G, B, segment=0)
+    assert set(int(i) for i in y["style"].argmax(1)) == set(range(6))
+    y.update(noise_seed=SEED, segment=0, clip_ids=list(range(B)))
+    out = d.ddim_sample_loop(m, (B, G.njoints, 1, G.n_poses), clip_denoised=False, model_kwargs={'y': y})
+    want = torch.from_numpy(gold["c3_sub"].astype(np.float32))
+    err = (out[:, ::8].cpu() - want).abs()
+    per_clip = err.amax(dim=(1, 2, 3))
+    rms = float(err.pow(2).mean().sqrt())
+    print(f"config 3: worst clip max err {float(per_clip.max()):.3g} (clip {int(per_clip.argmax())}), rms {rms:.3g}")
+    assert float(per_clip.max()) < 0.05 and rms < 0.008
+    # size-independent property over the FULL tensors: per-clip mean of the sample (fp64 sums from the reference)
+    mean_err = (out.double().sum(dim=(1, 2, 3)).cpu().numpy() - gold["c3_sum"]) / (G.njoints * G.n_poses)
+    assert np.abs(mean_err).max() < 2e-3, np.abs(mean_err).max()
+
+
+# ------------------------------------------------------------------------------------------------ a18: BEAT-TWH inference driver
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_beat_plus_inference_driver_vs_reference_golden(gold_dir, precision):
+    """BEAT-TWH-main/mydiffusion_beat_twh/sample.py:44-201 through the host mirror: 900 frames of features -> ceil(900/120) = 8
+    segments x 50 DDPM steps, velocity/acceleration seed, 1/2-1/2 first-frame blend, first J/3 channels, de-normalise —
+    against the reference's own `inference` (poses as handed to pose2bvh_bugfix)."""
+    from diffusestylegesture_b200 import sample_beat_twh as SB
+    gold = np.load(os.path.join(gold_dir, "r2_beat.npz"))
+    g = BEAT_PLUS
+    m = _plus_model(g, precision, max_batch=1)
+    d = create_gaussian_diffusion([50])
+    gen = torch.Generator().manual_seed(int(gold["inf/textaudio_seed"][0]))
+    textaudio = torch.randn(900, g.audio_dim, generator=gen)
+    args = SB.Config(dict(n_poses=g.n_poses, n_seed=g.n_seed, version="v0", name="DiffuseStyleGesture+"))
+    poses = SB.inference_batch_beat(args, textaudio, d.p_sample_loop, m, gold["inf/style"][None], gold["inf/seed_raw"][None],
+                                    seed=SEED, dataset='BEAT')[0]
+    assert poses.shape == gold["inf/poses"].shape == (900, g.njoints // 3)
+    mean, std = SB.load_stats('BEAT')
+    err_n = np.abs((poses - gold["inf/poses"]) / std)          # error in normalised units (std spans 1e-6 .. 0.53)
+    mx, rms = float(err_n.max()), float(np.sqrt((err_n ** 2).mean()))
+    print(f"beat+ inference {precision}: normalised max {mx:.3g} rms {rms:.3g}; de-normalised max {np.abs(poses - gold['inf/poses']).max():.3g}")
+    assert mx < (5e-3 if precision == "fp32" else 0.12) and rms < (1e-3 if precision == "fp32" else 0.015)
+
+
+def test_beat_plus_batch_equals_single_clips():
+    """Config 4 shape (batch of long-form clips): a batch of 3 clips with clip ids 5, 6, 7 == the three clips run alone."""
+    from diffusestylegesture_b200 import sample_beat_twh as SB
+    g = BEAT_PLUS
+    m = _plus_model(g, "bf16", max_batch=3)
+    d = create_gaussian_diffusion([4])
+    gen = torch.Generator().manual_seed(5)
+    ta = torch.randn(3, 300, g.audio_dim, generator=gen)                      # 300 frames -> 3 segments (ceil(300/120)), zero-padded
+    styles = np.array([[1, 0], [0, 1], [1, 0]], dtype=np.float32)
+    rng = np.random.default_rng(3)
+    mean, std = SB.load_stats('BEAT')
+    seeds = mean + std * np.cumsum(0.05 * rng.standard_normal((3, g.n_seed + 2, g.njoints // 3)), axis=1)
+    args = SB.Config(dict(n_poses=g.n_poses, n_seed=g.n_seed, version="v0", name="DiffuseStyleGesture+"))
+    full = SB.inference_batch_beat(args, ta, d.p_sample_loop, m, styles, seeds, seed=SEED, clip_ids=[5, 6, 7])
+    assert full.shape == (3, 300, g.njoints // 3)
+    for b in range(3):
+        one = SB.inference_batch_beat(args, ta[b], d.p_sample_loop, m, styles[b:b + 1], seeds[b:b + 1], seed=SEED, clip_ids=[5 + b])
+        assert np.abs(one[0] - full[b]).max() < 1e-5

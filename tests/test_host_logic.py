@@ -69,8 +69,15 @@ def test_mdm_state_dict_surface():
                  n_seed=g.n_seed, latent_dim=g.latent_dim, style_dim=g.style_in, source_audio_dim=g.audio_dim,
                  audio_feat_dim_latent=g.audio_latent)
         assert set(m2.state_dict()) >= {n for n, _ in state_dict_spec(g)}
+    from diffusestylegesture_b200.config import BEAT_PLUSPLUS
+    g = BEAT_PLUSPLUS                                     # "++": two more tensors (embed_text_last), audio over T - 2 n_seed frames
+    m5 = MDM(njoints=g.njoints, cond_mode='cross_local_attention5_style1_sample', audio_feat='wavlm', n_seed=g.n_seed,
+             latent_dim=g.latent_dim, style_dim=g.style_in, source_audio_dim=g.audio_dim, audio_feat_dim_latent=g.audio_latent)
+    assert m5.state_dict()["embed_text_last.weight"].shape == (g.audio_latent, g.njoints)
+    assert [n for n, _ in state_dict_spec(g)][-2:] == ["embed_text_last.weight", "embed_text_last.bias"]
+    assert g.audio_frames == g.n_poses - 2 * g.n_seed and BEAT_PLUS.audio_frames == 120
     with pytest.raises(NotImplementedError):
-        MDM(njoints=1141, cond_mode='cross_local_attention5_style1', audio_feat='wavlm', n_seed=8)
+        MDM(njoints=1141, cond_mode='cross_local_attention2_style1', audio_feat='wavlm', n_seed=8)
     with pytest.raises(NotImplementedError):
         MDM(njoints=1141, cond_mode='cross_local_attention3_style1', audio_feat='mfcc', n_seed=8)
 
@@ -78,12 +85,21 @@ def test_mdm_state_dict_surface():
 def test_unsupported_sampler_options_raise():
     d = create_gaussian_diffusion()
     m = MDM(njoints=1141, cond_mode='cross_local_attention3_style1', audio_feat='wavlm', n_seed=8)
-    for kw in ({"clip_denoised": True}, {"clip_denoised": False, "const_noise": True},
-               {"clip_denoised": False, "dump_steps": [1]}, {"clip_denoised": False, "cond_fn": lambda *a: 0}):
+    for kw in ({"clip_denoised": True}, {"clip_denoised": False, "randomize_class": True},
+               {"clip_denoised": False, "denoised_fn": lambda x: x}, {"clip_denoised": False, "cond_fn": lambda *a: 0}):
         with pytest.raises(NotImplementedError):
             d.p_sample_loop(m, (1, 1141, 1, 88), model_kwargs={'y': {}}, **kw)
     with pytest.raises(NotImplementedError):
         d.ddim_sample_loop(m, (1, 1141, 1, 88), clip_denoised=False, eta=0.5, model_kwargs={'y': {}})
+    # the reference's ddim_sample_loop raises NotImplementedError for these two (gaussian_diffusion.py:913-916); so do we
+    for kw in ({"dump_steps": [1]}, {"const_noise": True}):
+        with pytest.raises(NotImplementedError):
+            d.ddim_sample_loop(m, (1, 1141, 1, 88), clip_denoised=False, model_kwargs={'y': {}}, **kw)
+    with pytest.raises(ValueError):                       # plms_sample: 'order is invalid' (:1023-1024)
+        d.plms_sample_loop(m, (1, 1141, 1, 88), clip_denoised=False, model_kwargs={'y': {}}, order=7)
+    with pytest.raises(RuntimeError, match="no CPU path"):  # const_noise / dump_steps are engine options now: no CPU path
+        d.p_sample_loop(m, (1, 1141, 1, 88), clip_denoised=False, const_noise=True, dump_steps=[0],
+                        model_kwargs={'y': {'style': 0, 'seed': 0, 'audio': 0}})
 
 
 def test_bvh_tail_matches_reference_values(gold_dir, tmp_path):
@@ -244,5 +260,7 @@ def test_bench_reference_arm_contract():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["unit"] == "frames/s" and d["higher_is_better"] is True and d["n_gpus"] == 1
     assert d["metric"].startswith("motion frames/sec") and d["value"] > 0 and d["steps"] == 1 and d["warmup"] == 1
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    from oracle import build_ref                      # kind follows what is staged: the reference itself, else the oracle port
+    assert d["cpu_baseline"]["kind"] == ("reference" if build_ref.available() else "port")
+    assert d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
