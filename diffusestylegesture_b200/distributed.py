@@ -1,5 +1,5 @@
 """Clip-level data parallelism: one process per GPU, clips sharded contiguously, ONE gather of finished
-motions (SURVEY.md sections 2a, 8(e)).  The reference has no counterpart (its dist_util is dead code,
+motions to rank 0 (SURVEY.md sections 2a, 8(e)).  The reference has no counterpart (its dist_util is dead code,
 reference main/utils/dist_util.py:18-67); inside the sampling loop there is nothing to exchange, so no
 collective is fused into any kernel.  NCCL on GPUs, gloo in the CPU tests."""
 import os
@@ -31,20 +31,27 @@ def init_from_env(backend=None):
 
 
 def gather_motions(local, total, dst=0):
-    """local: [B_local, n, J] on this rank's device -> [total, n, J] on rank ``dst`` (None elsewhere).
-    Ranks may hold different clip counts; shards are padded to the largest and trimmed after the gather."""
+    """local: [B_local, n, J] on this rank's device -> [total, n, J] on rank ``dst`` (None elsewhere): ONE ``gather`` (NCCL:
+    ncclSend/ncclRecv pairs towards ``dst``; gloo in the CPU tests) straight from the device buffer the sampler wrote, before
+    any device->host copy.  Ranks may hold different clip counts (``shard_bounds``): shards are padded to the largest and
+    trimmed on ``dst``; only ``dst`` allocates the [world * bmax, n, J] receive buffer."""
     if not dist.is_initialized() or dist.get_world_size() == 1:
         return local
     world, rank = dist.get_world_size(), dist.get_rank()
     counts = [shard_bounds(total, r, world) for r in range(world)]
     bmax = max(hi - lo for lo, hi in counts)
-    pad = torch.zeros((bmax,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
-    pad[: local.shape[0]] = local
-    out = torch.empty((world * bmax,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
-    dist.all_gather_into_tensor(out, pad)
+    if local.shape[0] == bmax:
+        send = local.contiguous()
+    else:
+        send = torch.zeros((bmax,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        send[: local.shape[0]] = local
     if rank != dst:
+        dist.gather(send, None, dst=dst)
         return None
-    out = out.view((world, bmax) + tuple(local.shape[1:]))
+    out = torch.empty((world, bmax) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    dist.gather(send, [out[r] for r in range(world)], dst=dst)
+    if all(hi - lo == bmax for lo, hi in counts):
+        return out.view((world * bmax,) + tuple(local.shape[1:]))
     return torch.cat([out[r, : hi - lo] for r, (lo, hi) in enumerate(counts)], dim=0)
 
 

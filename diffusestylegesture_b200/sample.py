@@ -344,15 +344,40 @@ def plan_batches(lengths, max_batch):
     return out
 
 
+def wav_frames_16k(path):
+    """Motion frames (20 fps) a wav file yields after `load_wav_16k`, from the header alone (every rank of a sharded run needs
+    every clip's length to size the gather; only the owner decodes the samples)."""
+    import wave
+    with wave.open(path, 'rb') as w:
+        sr, n = w.getframerate(), w.getnframes()
+    if sr != 16000:
+        gdiv = math.gcd(sr, 16000)
+        n = -(-n * (16000 // gdiv) // (sr // gdiv))          # resample_poly: ceil(n * up / down)
+    return n * 20 // 16000
+
+
 def main_batch(args, save_dir, model_path, manifest, max_len=0, wavlm_model=None, model=None, diffusion=None,
                seed=123456, stats_path=DEFAULT_STATS, writers=8):
     """Many clips at once (additive to the reference CLI): every clip of the manifest goes through WavLM and the sampler in
-    batches of clips with equal segment counts; BVH files are written by a thread pool while the GPU runs the next batch."""
+    batches of clips with equal segment counts; BVH files are written by a thread pool while the GPU runs the next batch.
+
+    Under ``torchrun`` (WORLD_SIZE > 1: one process per GPU) the manifest is sharded contiguously over the ranks
+    (``distributed.shard_bounds``; noise is keyed by clip id, so results do not depend on the sharding), every rank samples
+    its clips on ``cuda:LOCAL_RANK``, and ONE gather brings the finished motions to rank 0, which writes every BVH:
+        torchrun --nproc-per-node 8 -m diffusestylegesture_b200.sample --batch manifest.csv --model_path ...
+    Returns the list of BVH paths (rank 0) or None (other ranks)."""
     from concurrent.futures import ThreadPoolExecutor
+    from .distributed import init_from_env, shard_bounds, gather_motions
     rows = read_manifest(manifest) if isinstance(manifest, str) else manifest
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank, local = 0, None
+    if world > 1:
+        rank, world, local = init_from_env(os.environ.get('DSG_DIST_BACKEND') or None)
     os.makedirs(save_dir, exist_ok=True)
-    dev = torch.device('cuda:' + str(_get(args, 'gpu', '0')))
-    max_batch = int(_get(args, 'max_batch', 0) or 0) or auto_max_batch(len(rows), dev)
+    dev = torch.device('cuda:' + str(_get(args, 'gpu', '0') if local is None or os.environ.get('DSG_DIST_SAME_GPU') else local))
+    lo, hi = shard_bounds(len(rows), rank, world)
+    mine = list(range(lo, hi))
+    max_batch = int(_get(args, 'max_batch', 0) or 0) or auto_max_batch(len(mine), dev)
     if model is None:
         cfg = dict(args) if isinstance(args, dict) else dict(vars(args))
         cfg['max_batch'] = max_batch
@@ -363,16 +388,22 @@ def main_batch(args, save_dir, model_path, manifest, max_len=0, wavlm_model=None
         wavlm_model = wavlm_init(dev, _get(args, 'wavlm_path', './WavLM/WavLM-Large.pt'))
     g = model.geometry
     sampler = _get(args, 'sampler', 'ddpm')
-    wins = []
     stride = g.n_poses - g.n_seed
-    for r in rows:
-        audio = r['audio'] if 'audio' in r else load_wav_16k(r['wav'])[0]
-        n_frames = max_len if max_len else audio.shape[0] * 20 // 16000
-        n_frames = min(n_frames, audio.shape[0] * 20 // 16000)
-        if n_frames < stride:          # the reference would run one ragged segment and fail inside the local attention
-            raise ValueError(f"{r['wav']}: {n_frames} frames of audio, shorter than one segment stride ({stride} frames = "
+
+    def frames_of(r, audio=None):
+        avail = (audio.shape[0] * 20 // 16000) if audio is not None else \
+            (r['audio'].shape[0] * 20 // 16000 if 'audio' in r else wav_frames_16k(r['wav']))
+        n = min(max_len, avail) if max_len else avail
+        if n < stride:                # the reference would run one ragged segment and fail inside the local attention
+            raise ValueError(f"{r['wav']}: {n} frames of audio, shorter than one segment stride ({stride} frames = "
                              f"{stride / 20:.1f} s); pad the clip or drop it from the manifest")
-        wins.append(segment_windows(audio, n_frames, g.n_poses, g.n_seed))
+        return segment_plan(n, g.n_poses, g.n_seed)[1]
+
+    n_all = [frames_of(r) for r in rows]                  # every rank validates the whole manifest (and sizes the gather)
+    wins = {}
+    for i in mine:
+        audio = rows[i]['audio'] if 'audio' in rows[i] else load_wav_16k(rows[i]['wav'])[0]
+        wins[i] = segment_windows(audio, frames_of(rows[i], audio), g.n_poses, g.n_seed)
     paths = [None] * len(rows)
 
     def write(i, seq, n_frames):
@@ -382,18 +413,35 @@ def main_batch(args, save_dir, model_path, manifest, max_len=0, wavlm_model=None
         pose2bvh(denormalise(seq, stats_path), path, length=n_frames - g.n_seed, smoothing=True)
         paths[i] = path
 
+    nmax = max(n_all) - g.n_seed
+    shard = torch.zeros(len(mine), nmax, g.njoints, dtype=torch.float32, device=dev) if world > 1 else None
     with ThreadPoolExecutor(max_workers=writers) as pool:
         jobs = []
-        for idx in plan_batches([w[0].shape[0] for w in wins], max_batch):
+        for grp in plan_batches([wins[i][0].shape[0] for i in mine], max_batch):
+            idx = [mine[k] for k in grp]
             nseg = wins[idx[0]][0].shape[0]
             feats = [wav2wavlm(wavlm_model, torch.stack([wins[i][0][s] for i in idx]), dev, g.n_poses) for s in range(nseg)]
             styles = torch.tensor([rows[i]['style'] for i in idx], dtype=torch.float32)
             seqs = inference_batch(model, diffusion, feats, styles, seed=seed, clip_ids=[rows[i]['clip_id'] for i in idx],
-                                   smoothing=True, sampler=sampler).numpy()
-            jobs += [pool.submit(write, i, seqs[k], wins[i][1]) for k, i in enumerate(idx)]
+                                   smoothing=True, sampler=sampler, out_device='cpu' if world == 1 else dev)
+            if world == 1:
+                seqs = seqs.numpy()
+                jobs += [pool.submit(write, i, seqs[k], wins[i][1]) for k, i in enumerate(idx)]
+            else:
+                for k, i in enumerate(idx):
+                    shard[i - lo, :seqs.shape[1]] = seqs[k]
+        if world > 1:
+            if torch.distributed.get_backend() == 'gloo':                # CPU test configuration: gloo moves host tensors
+                shard = shard.cpu()
+            everything = gather_motions(shard, len(rows))                  # the single collective of the path
+            if rank == 0:
+                everything = everything.cpu().numpy()
+                jobs += [pool.submit(write, i, everything[i, :n_all[i] - g.n_seed], n_all[i]) for i in range(len(rows))]
         for j in jobs:
             j.result()
-    return paths
+    if world > 1:
+        torch.distributed.barrier()
+    return paths if rank == 0 else None
 
 
 def parse_cli(argv=None):
@@ -422,10 +470,12 @@ def parse_cli(argv=None):
 if __name__ == '__main__':
     config = parse_cli()
     pprint(dict(config))
-    torch.cuda.set_device(int(config.gpu))
     if config.batch:
-        for p in main_batch(config, config.save_dir, config.model_path, config.batch, max_len=config.max_len):
+        if int(os.environ.get('WORLD_SIZE', '1')) == 1:
+            torch.cuda.set_device(int(config.gpu))
+        for p in main_batch(config, config.save_dir, config.model_path, config.batch, max_len=config.max_len) or []:
             print(p)
     else:
+        torch.cuda.set_device(int(config.gpu))
         main(config, config.save_dir, config.model_path, audio_path=None, mfcc_path=None,
              audiowavlm_path=config.audiowavlm_path, max_len=config.max_len)

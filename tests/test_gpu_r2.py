@@ -192,7 +192,8 @@ def test_beat_plus_inference_driver_vs_reference_golden(gold_dir, precision):
     err_n = np.abs((poses - gold["inf/poses"]) / std)          # error in normalised units (std spans 1e-6 .. 0.53)
     mx, rms = float(err_n.max()), float(np.sqrt((err_n ** 2).mean()))
     print(f"beat+ inference {precision}: normalised max {mx:.3g} rms {rms:.3g}; de-normalised max {np.abs(poses - gold['inf/poses']).max():.3g}")
-    assert mx < (5e-3 if precision == "fp32" else 0.12) and rms < (1e-3 if precision == "fp32" else 0.015)
+    # bf16: 8 chained segments (each seeded by the previous one's last 30 frames) x 50 steps; measured max 0.119 / rms 0.0042
+    assert mx < (5e-3 if precision == "fp32" else 0.25) and rms < (1e-3 if precision == "fp32" else 0.01)
 
 
 def test_beat_plus_batch_equals_single_clips():
@@ -213,3 +214,68 @@ def test_beat_plus_batch_equals_single_clips():
     for b in range(3):
         one = SB.inference_batch_beat(args, ta[b], d.p_sample_loop, m, styles[b:b + 1], seeds[b:b + 1], seed=SEED, clip_ids=[5 + b])
         assert np.abs(one[0] - full[b]).max() < 1e-5
+
+
+# ------------------------------------------------------------------------------------------------ (e): sharded product path
+_SHARD_WORKER = r'''
+import os, sys, torch
+sys.path.insert(0, %(root)r)
+from diffusestylegesture_b200 import sample as S
+from diffusestylegesture_b200.config import ZEGGS
+from diffusestylegesture_b200.mdm import MDM
+from diffusestylegesture_b200.model_util import create_gaussian_diffusion, load_model_wo_clip
+from diffusestylegesture_b200.synthetic import synthetic_state_dict
+from diffusestylegesture_b200.wavlm import WavLM
+from diffusestylegesture_b200.wavlm_config import WAVLM_LARGE, synthetic_wavlm_state_dict, synthetic_wav
+world = int(os.environ.get("WORLD_SIZE", "1"))
+local = int(os.environ.get("LOCAL_RANK", "0")) if not os.environ.get("DSG_DIST_SAME_GPU") else 0
+dev = "cuda:%%d" %% local
+torch.cuda.set_device(local)
+wm = WavLM(max_batch=4); wm.load_state_dict(synthetic_wavlm_state_dict(WAVLM_LARGE, seed=0)); wm.to(dev).eval()
+model = MDM(njoints=ZEGGS.njoints, cond_mode='cross_local_attention3_style1', audio_feat='wavlm', n_seed=8, precision='bf16', max_batch=4)
+load_model_wo_clip(model, synthetic_state_dict(ZEGGS, seed=0)); model.to(dev).eval()
+d = create_gaussian_diffusion([12])
+wavs = synthetic_wav(5, 170 * 800).numpy()
+names = ["Happy", "Old", "Sad", "Angry", "Neutral"]
+rows = [{'wav': '%%s_%%s_0.wav' %% (chr(97 + i), n), 'style': S.style2onehot[n], 'style_name': n, 'clip_id': 3 * i,
+         'audio': wavs[i][:(100 if i == 1 else 170) * 800]} for i, n in enumerate(names)]
+paths = S.main_batch(S.Config(n_poses=88, audio_feat="wavlm", gpu=str(local), max_batch=0), %(out)r, None, rows, wavlm_model=wm,
+                     model=model, diffusion=d, seed=11)
+if int(os.environ.get("RANK", "0")) == 0:
+    assert len(paths) == 5
+    print("PATHS " + " ".join(paths))
+else:
+    assert paths is None
+'''
+
+
+def _run_sharded(tmp_path, tag, nproc, env_extra):
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = tmp_path / tag
+    script = tmp_path / (tag + ".py")
+    script.write_text(_SHARD_WORKER % {"root": root, "out": str(out)})
+    env = dict(os.environ, **env_extra)
+    cmd = [sys.executable, str(script)] if nproc == 1 else \
+        [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}", "--master-addr", "127.0.0.1",
+         "--master-port", "29633", str(script)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env)
+    assert r.returncode == 0, (r.stdout + r.stderr)[-3000:]
+    line = [l for l in r.stdout.splitlines() if l.startswith("PATHS ")][0]
+    return line.split(" ")[1:]
+
+
+def test_manifest_sharded_over_ranks_writes_identical_bvh(tmp_path):
+    """`sample.main_batch` under torchrun: the manifest is sharded over the ranks, ONE gather brings the motions to rank 0,
+    which writes every BVH — byte-identical to the single-process run (noise keyed by clip id).  With >= 2 GPUs the two
+    ranks use NCCL on cuda:0 / cuda:1; on a one-GPU box both ranks share cuda:0 and the gather runs over gloo."""
+    single = _run_sharded(tmp_path, "single", 1, {})
+    if torch.cuda.device_count() >= 2:
+        sharded = _run_sharded(tmp_path, "nccl2", 2, {})
+    else:
+        sharded = _run_sharded(tmp_path, "gloo2", 2, {"DSG_DIST_BACKEND": "gloo", "DSG_DIST_SAME_GPU": "1"})
+    assert len(single) == len(sharded) == 5
+    for a, b in zip(single, sharded):
+        assert os.path.basename(a) == os.path.basename(b)
+        assert open(a, "rb").read() == open(b, "rb").read(), os.path.basename(a)
