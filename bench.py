@@ -11,7 +11,11 @@ B clips; clips are independent, so there is no data-path collective — only the
 
 `value`  : frames/s with conditioning features already resident in HBM, result left on the device.
 `e2e`    : frames/s through the public API (sample.inference_batch) with pinned HOST feature buffers (H2D of
-           each segment's features inside the timed region) and the D2H read of the finished motions.
+           each segment's features inside the timed region), at N > 1 the ONE gather of all finished motions to
+           rank 0 (distributed.gather_motions, from the device buffers), and the D2H read of the result.
+`sweep`  : (N = 1) the same step at B in {1, 8, 64, 256, 512} clips (BASELINE config 5);  `config3`: B = 64, DDIM-100,
+           six styles (BASELINE config 3);  `strong` (N > 1): 512 clips sharded over the N ranks (strong scaling).
+`parity` : clip 0 of the timed run against the committed 1000-step reference golden (tests/golden).
 `roofline`: dominant kernel class, algorithmic FLOPs / CUDA-event time measured in a separate profiled pass.
 `cpu_baseline`: the oracle port of the reference (torch fp32 CPU, all host threads), bounded sample.
 """
@@ -274,6 +278,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--profile-steps", type=int, default=40)
+    ap.add_argument("--no-sweep", action="store_true", help="skip the batch sweep / config 3 / strong-scaling side measurements")
     ap.add_argument("--no-wavlm", action="store_true", help="skip the side measurement of the WavLM-Large conditioning forward")
     ap.add_argument("--wavlm-batch", type=int, default=32)
     args = ap.parse_args()
@@ -338,9 +343,26 @@ def main():
         return S.inference_batch(model, diffusion, feats, styles_pin if out_device == "cpu" else styles, seed=123456,
                                  clip_ids=clip_ids, out_device=out_device, out=out_pin if out_device == "cpu" else None)
 
-    def timed(feats, out_device, K, W):
+    out_all_pin = torch.empty(world * B, n_frames - g.n_seed, g.njoints, dtype=torch.float32).pin_memory() \
+        if (world > 1 and rank == 0 and not args.no_e2e) else None
+
+    def e2e_step(feats, _unused):
+        """host features -> motions in HOST memory on rank 0.  N = 1: straight into the caller's pinned buffer.  N > 1: every
+        rank samples into device memory, ONE gather to rank 0 (NCCL, from the device buffers), rank 0 reads the result."""
+        if world == 1:
+            return one_step(feats, "cpu")
+        loc = S.inference_batch(model, diffusion, feats, styles_pin, seed=123456, clip_ids=clip_ids, out_device=dev)
+        allm = gather_motions(loc, world * B)
+        if rank == 0:
+            out_all_pin.copy_(allm, non_blocking=True)
+            torch.cuda.current_stream(dev).synchronize()
+            return out_all_pin
+        return loc
+
+    def timed(feats, out_device, K, W, step_fn=None):
+        step_fn = step_fn or one_step
         for _ in range(W):
-            one_step(feats, out_device)
+            step_fn(feats, out_device)
         torch.cuda.synchronize(dev)
         if world > 1:
             dist.barrier()
@@ -350,7 +372,7 @@ def main():
             flush.add_(1.0)                                    # L2 flush between timed iterations (untimed)
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
-            out = one_step(feats, out_device)
+            out = step_fn(feats, out_device)
             b.record()
             torch.cuda.synchronize(dev)
             total += a.elapsed_time(b)
@@ -372,13 +394,82 @@ def main():
 
     e2e = None
     if not args.no_e2e:
-        e_ms, _, out_h = timed(feats_pin, "cpu", args.steps, 1)
+        e_ms, _, out_h = timed(feats_pin, "cpu", args.steps, 1, step_fn=e2e_step)
         log("e2e done: %.1f ms/step" % (e_ms / args.steps))
-        gathered = gather_motions(out_h.to(dev), world * B)              # the single collective of the path
         e2e = {"value": frames_all / (e_ms / args.steps * 1e-3), "unit": UNIT,
                "h2d_bytes_per_step": int(sum(f.numel() * 4 for f in feats_pin) + styles_pin.numel() * 4),
-               "d2h_bytes_per_step": int(out_h.numel() * 4)}
-        assert rank != 0 or gathered.shape[0] == world * B
+               "d2h_bytes_per_step": int(out_h.numel() * 4) if rank == 0 else 0,
+               "collective": None if world == 1 else f"one gather of [{B}, {n_frames - g.n_seed}, {g.njoints}] fp32 per rank to rank 0 "
+                                                     f"(NCCL, {world} ranks), inside the timed region; the D2H of all "
+                                                     f"{world * B} motions is rank 0's"}
+        assert rank != 0 or out_h.shape[0] == world * B
+
+    # ---- parity tie: clip 0 of the run just timed (global clip id 0, seed 123456, style 0, synthetic features) IS the clip of
+    # tests/golden/inference_zeggs_1000.npz (the reference's own 4-segment x 1000-step run): its noise is keyed by clip id, so
+    # it must come out the same whatever the batch around it was.  Compared in normalised units.
+    parity = None
+    if rank == 0 and nseg == 4 and diffusion.num_timesteps == 1000:
+        gp = os.path.join(ROOT, "tests", "golden", "inference_zeggs_1000.npz")
+        sp = os.path.join(ROOT, "tests", "golden", "zeggs_mean_std.npz")
+        if os.path.exists(gp) and os.path.exists(sp):
+            gold, st = np.load(gp), np.load(sp)
+            if np.array_equal(np.asarray(gold["style"], dtype=np.float32), styles[0].numpy()):
+                std = np.clip(np.array(st["std"]).squeeze(), 0.01, None)
+                want = (gold["poses"] - np.array(st["mean"]).squeeze()) / std
+                got = out[0].float().cpu().numpy()
+                err = np.abs(got - want)
+                tol = (0.15, 0.02) if precision == "bf16" else (5e-3, 5e-4)
+                parity = {"clip0_vs_reference_golden": {"max": float(err.max()), "rms": float(np.sqrt((err ** 2).mean())),
+                                                        "tolerance_max_rms": list(tol), "units": "normalised motion (|x| <~ 3)",
+                                                        "golden": "tests/golden/inference_zeggs_1000.npz (reference sample.inference)"}}
+                parity["ok"] = bool(err.max() < tol[0] and np.sqrt((err ** 2).mean()) < tol[1])
+                log("parity: clip 0 vs reference golden: max %.4g rms %.4g (%s)" % (err.max(), np.sqrt((err ** 2).mean()), parity["ok"]))
+                if not np.isfinite(err).all() or err.max() > 1.0:
+                    raise SystemExit("bench: clip 0 of the timed run does not match the reference golden: %r" % (parity,))
+
+    # ---- BASELINE config 5 (batch sweep, N = 1), config 3 (B = 64, DDIM-100, six styles), strong scaling (N > 1)
+    def quick(Bq, diff, sampler="ddpm", offset=0):
+        """one warm-up + one timed step of Bq clips on this rank (device-resident features)."""
+        cq = [synthetic_conditioning(g, Bq, segment=s_, clip_offset=offset) for s_ in range(nseg)]
+        fq = [c["audio"].to(dev) for c in cq]
+        ids = list(range(offset, offset + Bq))
+
+        def run():
+            return S.inference_batch(model, diff, fq, cq[0]["style"], seed=123456, clip_ids=ids, out_device=dev, sampler=sampler)
+        run()
+        torch.cuda.synchronize(dev)
+        flush.add_(1.0)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        o = run()
+        b.record()
+        torch.cuda.synchronize(dev)
+        assert bool(torch.isfinite(o).all())
+        return a.elapsed_time(b)
+
+    sweep, config3, strong = None, None, None
+    if precision == "bf16" and not args.no_sweep:
+        if world == 1:
+            sweep = []
+            for Bq in (1, 8, 64, 256, 512):
+                ms = quick(Bq, diffusion)                     # (the engine is rebuilt for a larger workspace when Bq > B)
+                sweep.append({"clips": Bq, "ms_per_step": ms, "value": Bq * n_frames / (ms * 1e-3), "unit": UNIT})
+                log("sweep: B=%d  %.1f ms  %.0f frames/s" % (Bq, ms, sweep[-1]["value"]))
+            d3 = create_gaussian_diffusion("ddim100")
+            ms = quick(64, d3, sampler="ddim")
+            config3 = {"workload": "batch 64 ZEGGS 320-frame clips, styles i mod 6, DDIM-100 (eta 0), 4 segments", "clips": 64,
+                       "ms_per_step": ms, "value": 64 * n_frames / (ms * 1e-3), "unit": UNIT,
+                       "parity": "tests/test_gpu_r2.py::test_config3_b64_ddim100_six_styles_vs_reference_golden"}
+            log("config 3: %.1f ms, %.0f frames/s" % (ms, config3["value"]))
+            eng = model.get_engine(B)                        # the live engine (rebuilt by the 512-clip point)
+        else:
+            G_ = 512
+            from diffusestylegesture_b200.distributed import shard_bounds
+            lo, hi = shard_bounds(G_, rank, world)
+            dist.barrier()
+            ms = barrier_max_ms(quick(hi - lo, diffusion, offset=lo), dev)
+            strong = {"global_clips": G_, "clips_per_gpu": hi - lo, "ms_per_step": ms, "value": G_ * n_frames / (ms * 1e-3), "unit": UNIT,
+                      "scaling": "strong", "note": "512 clips sharded contiguously over the ranks (max over ranks), device-resident"}
 
     # ---- roofline.  The bf16 engine runs a segment as ONE persistent kernel (csrc/dsg_clip_kernel.cuh), so "the
     # dominant kernel" is that kernel: its launch is timed live with CUDA events on the launching stream, and
@@ -414,8 +505,13 @@ def main():
             # pre-drawn noise written and read once per clip-step (everything else is on chip or L2-resident weights): ncu
             # measured 1.95 MB per clip-step (profiles/r01_clip_kernel_v6_ncu_full_summary.csv: dram read + write of a
             # 148-clip x 12-step launch = 3.458 GB)
-            roofline["traffic"] = 1.947e6 * B * diffusion.num_timesteps
-            roofline["traffic_note"] = "bytes per launch = ncu dram__bytes_read+write per clip-step (1.95 MB, r01 v6 capture) x clips x steps"
+            # (an ncu --set full capture of this kernel, summarised by profiles/summarise_ncu.py into profiles/clip_kernel_traffic.json)
+            tp = os.path.join(ROOT, "profiles", "clip_kernel_traffic.json")
+            if os.path.exists(tp):
+                tj = json.load(open(tp))
+                roofline["traffic"] = tj["dram_bytes_per_clip_step"] * B * diffusion.num_timesteps
+                roofline["traffic_note"] = ("bytes per launch = ncu dram__bytes_read.sum + dram__bytes_write.sum per clip-step (%.3g MB, %s) "
+                                            "x clips x steps of this launch" % (tj["dram_bytes_per_clip_step"] / 1e6, tj["source"]))
             log("clip-kernel segment: %.1f ms (%.1f us per DDPM step), %.1f TFLOP/s" % (ms, ms * 1e3 / diffusion.num_timesteps, ach))
             try:      # where the persistent kernel spends its cycles (instrumented build of the same kernel, 50 steps)
                 os.environ["DSG_CLIP_PROF"] = "1"
@@ -488,7 +584,7 @@ def main():
                            "clips_per_gpu": B, "global_clips": world * B, "segments": nseg, "ddpm_steps": diffusion.num_timesteps,
                            "precision": precision, "parallelism": f"clip-dp{world}", "l2": "flushed between timed iterations (256 MB write)"},
                 "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "kernels": kernels, "wavlm": wavlm,
-                "cpu_baseline": cb, "clocks": clk}
+                "cpu_baseline": cb, "clocks": clk, "parity": parity, "sweep": sweep, "config3": config3, "strong": strong}
         emit(line)
     if world > 1:
         dist.barrier()

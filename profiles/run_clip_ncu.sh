@@ -20,6 +20,6 @@ for _ in range(2):
     d.p_sample_loop(m, (B, g.njoints, 1, g.n_poses), clip_denoised=False, model_kwargs={'y': y})
 torch.cuda.synchronize()
 PY
-ncu --set full --clock-control none --import-source on -k regex:clip_kernel -s 1 -c 1 -o gpurun_out/clip_kernel_r01_v6 -f python /tmp/clip_once.py > gpurun_out/ncu_clip.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:clip_kernel -s 1 -c 1 -o gpurun_out/clip_kernel_r02 -f python /tmp/clip_once.py > gpurun_out/ncu_clip.log 2>&1
 tail -3 gpurun_out/ncu_clip.log
-ls -la gpurun_out/clip_kernel_r01_v6.ncu-rep
+ls -la gpurun_out/clip_kernel_r02.ncu-rep
