@@ -226,6 +226,99 @@ def bench_wavlm(dev, batch, peaks, frames_per_s_per_gpu, pipeline=None):
     return res
 
 
+def bench_plus(args):
+    """BASELINE config 4: DiffuseStyleGesture+ long-form clips (900 frames = 8 chained segments of 150 frames, stride 120,
+    1000-step DDPM) through the BEAT-TWH driver mirror (sample_beat_twh.inference_batch_beat) on the tcgen05 multi-kernel
+    path (D = 384 / 512), `--batch` clips per GPU (default 8: batch 32 over 4 GPUs), one gather to rank 0 at N > 1."""
+    from diffusestylegesture_b200.distributed import init_from_env, barrier_max_ms, gather_motions
+    from diffusestylegesture_b200.config import BEAT_PLUS, TWH_PLUS
+    from diffusestylegesture_b200.mdm import MDM
+    from diffusestylegesture_b200.model_util import create_gaussian_diffusion, load_model_wo_clip
+    from diffusestylegesture_b200.synthetic import synthetic_state_dict
+    from diffusestylegesture_b200 import sample_beat_twh as SB
+    import torch.distributed as dist
+    rank, world, local = init_from_env()
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    g = BEAT_PLUS if args.workload == "beat+" else TWH_PLUS
+    dataset = "BEAT" if args.workload == "beat+" else "TWH"
+    flop_clip_step = 4_184.4e6 if args.workload == "beat+" else 6_312.1e6          # SURVEY.md section 8(d)
+    B = args.batch or 8
+    n_frames, steps = 900, args.ddpm_steps
+    model = MDM(njoints=g.njoints, cond_mode='cross_local_attention4_style1_sample', audio_feat='wavlm', n_seed=g.n_seed,
+                latent_dim=g.latent_dim, style_dim=g.style_in, source_audio_dim=g.audio_dim, audio_feat_dim_latent=g.audio_latent,
+                precision="bf16", max_batch=B)
+    load_model_wo_clip(model, synthetic_state_dict(g, seed=0))
+    model.to(dev).eval()
+    diffusion = create_gaussian_diffusion('' if steps == 1000 else [steps])
+    cfg = SB.Config(dict(n_poses=g.n_poses, n_seed=g.n_seed, version="v0", name="DiffuseStyleGesture+"))
+    gen = torch.Generator().manual_seed(1234 + rank)
+    ta_pin = torch.randn(B, n_frames, g.audio_dim, generator=gen).pin_memory()
+    ta_dev = ta_pin.to(dev)
+    styles = np.zeros((B, g.style_in), dtype=np.float32)
+    styles[np.arange(B), (rank * B + np.arange(B)) % g.style_in] = 1
+    mean, std = SB.load_stats(dataset)
+    seeds = mean + std * np.cumsum(0.05 * np.random.default_rng(3).standard_normal((g.n_seed + 2, g.njoints // 3)), axis=0)
+    ids = list(range(rank * B, rank * B + B))
+    eng = model.get_engine(B)
+
+    def step(ta, e2e):
+        out = SB.inference_batch_beat(cfg, ta, diffusion.p_sample_loop, model, styles, seeds, seed=123456, dataset=dataset,
+                                      clip_ids=ids, out_device=dev)
+        if e2e:
+            allm = gather_motions(out.contiguous(), world * B)
+            return allm.cpu() if rank == 0 else None
+        return out
+
+    def timed(ta, e2e, K, W):
+        for _ in range(W):
+            step(ta, e2e)
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        l0 = eng.launches
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(K):
+            out = step(ta, e2e)
+        b.record()
+        torch.cuda.synchronize(dev)
+        return barrier_max_ms(a.elapsed_time(b), dev) / K, eng.launches - l0, out
+
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    ms, launches, out = timed(ta_dev, False, args.steps, args.warmup)
+    clk = clocks.stop() if rank == 0 else None
+    e_ms, _, out_h = timed(ta_pin, True, max(1, args.steps // 2), 1)
+    if rank == 0:
+        peaks = load_peaks()
+        nseg = 8
+        ach = flop_clip_step * B * steps * nseg / (ms * 1e-3) / 1e12
+        frames = world * B * n_frames
+        line = {"metric": "motion frames/sec (1000-step DDPM, 900-frame DiffuseStyleGesture+ clips)", "value": frames / (ms * 1e-3),
+                "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": f"{args.workload} (D={g.latent_dim}, J={g.njoints}, T=150): 900-frame clips = 8 chained segments, "
+                                       f"{steps}-step DDPM, {B} clips per GPU, synthetic features [B,900,{g.audio_dim}] and weights",
+                           "clips_per_gpu": B, "global_clips": world * B, "segments": nseg, "ddpm_steps": steps, "precision": "bf16",
+                           "parallelism": f"clip-dp{world}", "l2": "working set (weights 27-41 MB bf16 + activations) re-streamed every step; "
+                                                                    "8000 kernel-graph replays per timed step"},
+                "e2e": {"value": frames / (e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(ta_pin.numel() * 4),
+                        "d2h_bytes_per_step": int(out_h.numel() * 4),
+                        "collective": None if world == 1 else "one gather of the finished motions to rank 0 inside the timed region"},
+                "gpu_launches": int(launches),
+                "roofline": {"kernel": "multi-kernel tcgen05 path (44 kernels per DDPM step, CUDA-graph replay)", "bound": "tensor",
+                             "achieved": ach, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                             "frac": ach / peaks["bf16_tflops_sustained"], "traffic": None,
+                             "peak_source": peaks["source"] + ", sustained bf16", "us_per_ddpm_step": ms * 1e3 / (steps * nseg)},
+                "cpu_baseline": None, "clocks": clk}
+        emit(line)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def emit(line):
     """The ONE JSON line goes to the real stdout; everything else that lands on fd 1 (NCCL's version banner, library
     prints) was redirected to stderr in main()."""
@@ -278,6 +371,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--profile-steps", type=int, default=40)
+    ap.add_argument("--workload", default="zeggs", choices=["zeggs", "beat+", "twh+"],
+                    help="zeggs = the metric's configuration (default); beat+ / twh+ = BASELINE config 4 (900-frame long-form clips)")
     ap.add_argument("--no-sweep", action="store_true", help="skip the batch sweep / config 3 / strong-scaling side measurements")
     ap.add_argument("--no-wavlm", action="store_true", help="skip the side measurement of the WavLM-Large conditioning forward")
     ap.add_argument("--wavlm-batch", type=int, default=32)
@@ -289,6 +384,9 @@ def main():
         run_reference(args, rank, int(os.environ.get("WORLD_SIZE", "1")))
         return
 
+    if args.workload != "zeggs":
+        bench_plus(args)
+        return
     rank, world, local = init_from_env()
     assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
     if not torch.cuda.is_available():
@@ -332,6 +430,12 @@ def main():
     clip_ids = list(range(clip0, clip0 + B))
     conds = [synthetic_conditioning(g, B, segment=s, clip_offset=clip0) for s in range(nseg)]
     styles = conds[0]["style"]
+    # global clip 0 is the clip of the committed reference golden (tests/golden/inference_zeggs_1000.npz: clip id 0, its
+    # synthetic features, seed 123456): it carries that clip's style instead of 0 mod 6, so that the TIMED output itself
+    # can be checked against the reference (`parity` in the JSON line)
+    gold_path = os.path.join(ROOT, "tests", "golden", "inference_zeggs_1000.npz")
+    if rank == 0 and os.path.exists(gold_path):
+        styles[0] = torch.from_numpy(np.asarray(np.load(gold_path)["style"], dtype=np.float32))
     feats_dev = [c["audio"].to(dev) for c in conds]
     feats_pin = [c["audio"].pin_memory() for c in conds]
     styles_pin = styles.pin_memory()

@@ -104,8 +104,10 @@ def test_noise_stream_matches_oracle_stream(eng):
     eng.set_schedule("ddpm", coef, qs, tmap)
     shp = (G.njoints, 1, G.n_poses)
     x = torch.zeros((2,) + shp).cuda()
-    got = eng.posterior_step(x, torch.zeros_like(x), 5, 987654321012345, clip_ids=[3, 2 ** 33 + 1], segment=2, draw=77)
-    want = O.noise_tensor(987654321012345, [3, 2 ** 33 + 1], 2, 77, shp)
+    got = eng.posterior_step(x, torch.zeros_like(x), 5, 987654321012345, clip_ids=[3, 2 ** 32 - 1], segment=2, draw=77)
+    want = O.noise_tensor(987654321012345, [3, 2 ** 32 - 1], 2, 77, shp)
+    with pytest.raises(RuntimeError, match="clip id"):             # ids are 32-bit counter words: 2^32 + k would alias clip k
+        eng.posterior_step(x, torch.zeros_like(x), 5, 1, clip_ids=[3, 2 ** 32 + 1], segment=2, draw=77)
     assert _maxdiff(got, want) < 6e-5
     assert float((got.cpu() - want).abs().mean()) < 1e-6
     assert abs(float(got.mean())) < 0.01 and abs(float(got.std()) - 1) < 0.01
