@@ -65,7 +65,17 @@ constexpr int R_LAYER = 2048, R_QKV = 0, R_WO = 768, R_W1 = 1024, R_HEAD = NL * 
 // barrier indices
 enum { B_WFULL = 0, B_WEMPTY = 4, B_AFULL = 8, B_AEMPTY = 12, B_ACCR = 16, B_ACCF = 20, B_XSR = 24, B_BUFR = 25, B_BUFF = 27,
        B_ZR = 29, B_ZF = 30, B_HFULL = 31, B_HEMPTY = 35, B_HGO = 39, B_XAR = 40, B_QKR = 41, B_SR = 42, B_PR = 43, B_OR = 44,
-       B_COUNT = 45 };
+       B_W2FULL = 45, B_W2EMPTY = 50, B_COUNT = 55 };
+// FFN (round 2): the GELU'd hidden chunk never touches shared memory.  The epilogue writes it (fp16 pairs) back over the first
+// 64 columns of its own linear1 accumulator quarter with tcgen05.st, and linear2 reads it from there as a TENSOR-MEMORY A
+// operand (tcgen05.mma [d], [a_tmem], b_desc): no st.shared / proxy fence in the epilogue, no A re-reads by the tensor core, and
+// BUF + the attention staging area are free during the FFN: they are the 5-stage ring of the linear2 weight tiles (80 KB),
+// fed by the attention issuer's thread, so that a linear2 tile waiting for its GELU chunk never blocks the linear1 stream.
+// K order inside a 128-unit chunk: TMEM column j holds units (j, 64 + j) -> K positions (2j, 2j + 1); the linear2 slab is
+// packed in that order (pack_w2_perm_kernel), so every epilogue thread overwrites only columns it has read itself.
+constexpr int NS2 = 5;
+DSG_DEVINL int w2stage_off(int slot) { return slot < 2 ? OFF_Q + slot * WSTAGE : OFF_BUF + (slot - 2) * KT; }
+static_assert(2 * WSTAGE <= AT_BYTES, "two linear2 stages live in the attention staging area");
 
 struct ClipParams {
   float* x;                 // [B][J][T] fp32, in/out
@@ -97,6 +107,22 @@ DSG_DEVINL void tmem_ld8_issue(uint32_t taddr, float* v) {
   uint32_t* r = reinterpret_cast<uint32_t*>(v);
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr));
+}
+DSG_DEVINL void tmem_st16(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};\n" ::"r"(taddr),
+               "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+               "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem]^T: the A operand is read from tensor memory (lanes = rows, 16-bit elements packed two per
+// 32-bit column, K-major), B through a shared-memory descriptor
+DSG_DEVINL void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
 DSG_DEVINL void tie4(float* v) { asm volatile("" : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]) :: "memory"); }
 DSG_DEVINL void ldsm_x2(uint32_t& r0, uint32_t& r1, const void* p) {
@@ -154,7 +180,8 @@ DSG_DEVINL void unpack8(const uint4 u, float* v) {
 // cycle counters (CTA 0): where each role spends its time
 enum { PF_TOTAL = 0, PF_MMA_WAIT_W, PF_MMA_WAIT_OTHER, PF_PROD_WAIT_EMPTY, PF_W_STAGE, PF_W_IN_WAIT, PF_W_IN_EPI, PF_W_LOCAL,
        PF_W_QKV_WAIT, PF_W_ATT, PF_W_LN_WAIT, PF_W_LN, PF_W_GELU_WAIT, PF_W_GELU, PF_W_HEAD_WAIT, PF_W_HEAD, PF_W_ZWAIT,
-       PF_W_EXTRACT, PF_W_SYNC1, PF_W_ATT_MMA, PF_W_ATT_MERGE, PF_COUNT };
+       PF_W_EXTRACT, PF_W_SYNC1, PF_W_ATT_MMA, PF_W_ATT_MERGE,
+       PF_MMA_FFN_TOTAL, PF_MMA_FFN_WAIT_W, PF_MMA_FFN_WAIT_O, PF_MMA_QKV_TOTAL, PF_MMA_QKV_WAIT_W, PF_MMA_QKV_WAIT_O, PF_COUNT };
 
 // consumers of tcgen05.ld results must not be scheduled above tcgen05.wait::ld: pass the registers through an empty
 // volatile asm placed after the wait
@@ -219,6 +246,7 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
     mbar_init(&bars[B_ZR], 1); mbar_init(&bars[B_ZF], NW);
     mbar_init(&bars[B_HGO], 1); mbar_init(&bars[B_XAR], NW);
     mbar_init(&bars[B_QKR], NW); mbar_init(&bars[B_SR], 1); mbar_init(&bars[B_PR], NW); mbar_init(&bars[B_OR], 1);
+    for (int i = 0; i < NS2; ++i) { mbar_init(&bars[B_W2FULL + i], 1); mbar_init(&bars[B_W2EMPTY + i], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_in) : "memory");
@@ -284,14 +312,7 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
             for (int nh = 0; nh < 2; ++nh)
               for (int kb = 0; kb < 4; ++kb) load(&tm_w128, rb + R_WO + nh * 128, kb * 64, WSTAGE);
             auto ff1 = [&](int c) { for (int kb = 0; kb < 4; ++kb) load(&tm_w128, rb + R_W1 + c * 128, kb * 64, WSTAGE); };
-            // linear1 chunk c+2 goes BEFORE linear2 chunk c: it only needs GELU(c) to have read its accumulator (early),
-            // so the tensor core and the weight stream keep running while GELU(c) computes
-            ff1(0); ff1(1);
-            for (int c = 0; c < 8; ++c) {
-              if (c + 2 < 8) ff1(c + 2);
-              for (int nh = 0; nh < 2; ++nh)
-                for (int kb2 = 0; kb2 < 2; ++kb2) load(&tm_w2, l * 256 + nh * 128, c * 128 + kb2 * 64, WSTAGE);
-            }
+            for (int c = 0; c < 8; ++c) ff1(c);          // (the linear2 tiles travel through their own ring: see the attention issuer)
           }
           // pose head: weights + the x_t / z chunks the posterior needs (BUF is free once the last linear2 has completed)
           for (int kb = 0; kb < 4; ++kb) load(&tm_w128, R_HEAD, kb * 64, WSTAGE);
@@ -323,7 +344,7 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
       const uint32_t xs_addr = smem_u32(smem + OFF_XS), buf_addr = smem_u32(smem + OFF_BUF), smem_addr0 = smem_u32(smem);
       constexpr uint32_t idesc128 = make_idesc_bf16(128, 128), idesc64 = make_idesc_bf16(128, 64), idesc128h = make_idesc_f16(128, 128);
       // one weight tile: 4 UMMAs (K = 64) of A k-tile `a_tile` against the current stage
-      long long t_w = 0, t_o = 0;
+      long long t_w = 0, t_o = 0, t_ffn = 0, t_ffn_w = 0, t_ffn_o = 0, t_qkv = 0, t_qkv_w = 0, t_qkv_o = 0;
       const bool prof = PROF && P.prof != nullptr && blockIdx.x == 0;
       const long long t_begin = clock64();
       auto tile = [&](uint32_t a_tile, uint32_t d_col, uint32_t idesc, bool acc_first, uint32_t a_sbo = 1024) {
@@ -337,6 +358,20 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
           umma_bf16(tmem + d_col, make_sw128_desc_sbo(a_tile + kk * 32, a_sbo), make_sw128_desc(b_tile + kk * 32), idesc, (acc_first || kk > 0) ? 1u : 0u);
         tcgen05_commit(&bars[B_WEMPTY + slot]);
         slot = (slot + 1 == NS) ? 0 : slot + 1;
+      };
+      int slot2 = 0;
+      // a linear2 tile: B from the linear2 ring, A = the fp16 hidden chunk in tensor memory (8 columns per K = 16 step)
+      auto tile2 = [&](uint32_t a_tmem, uint32_t d_col, uint32_t idesc, bool acc_first) {
+        const long long c0 = prof ? clock64() : 0;
+        ph.wait(bars, B_W2FULL + slot2);
+        if (prof) t_w += clock64() - c0;
+        tcgen05_fence_after();
+        const uint32_t b_tile = smem_addr0 + w2stage_off(slot2);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+          umma_ts(tmem + d_col, tmem + a_tmem + kk * 8, make_sw128_desc(b_tile + kk * 32), idesc, (acc_first || kk > 0) ? 1u : 0u);
+        tcgen05_commit(&bars[B_W2EMPTY + slot2]);
+        slot2 = (slot2 + 1 == NS2) ? 0 : slot2 + 1;
       };
       auto owait = [&](int id) { const long long c0 = prof ? clock64() : 0; ph.wait(bars, id); if (prof) t_o += clock64() - c0; };
       for (int clip = blockIdx.x; clip < P.B; clip += gridDim.x)
@@ -354,6 +389,7 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
             // ---- in_proj, one head at a time into alternating TMEM halves: q | k | v = 3 x 64 columns
             owait(B_XSR);
             tcgen05_fence_after();
+            const long long qkv_t0 = prof ? clock64() : 0, qkv_w0 = t_w, qkv_o0 = t_o;
             auto qkv = [&](int h) {
               const int hb = h & 1;
               owait(B_ACCF + 2 * hb); owait(B_ACCF + 2 * hb + 1);
@@ -365,6 +401,7 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
             // (S = Q K^T and O = P V of every head are issued by the attention issuer, warp 15; a head's TMEM half comes back
             //  after its O epilogue, which is what in_proj(h + 2) waits for)
             for (int h = 0; h < NH; ++h) qkv(h);
+            if (prof) { t_qkv += clock64() - qkv_t0; t_qkv_w += t_w - qkv_w0; t_qkv_o += t_o - qkv_o0; }
             // ---- out_proj: A = attention output in BUF, D = Q0|Q1
             owait(B_BUFR + 0); owait(B_BUFR + 1);
             owait(B_ACCF + 0); owait(B_ACCF + 1);
@@ -376,23 +413,26 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
             // ---- FFN: linear1 in 8 chunks of 128 hidden units (D = Q2 / Q3 alternating), linear2 accumulates into Q0|Q1
             owait(B_XSR);
             tcgen05_fence_after();
-            auto ff1 = [&](int c) {
-              owait(B_ACCF + 2 + (c & 1));
-              tcgen05_fence_after();
+            // linear1(c) -> quarter 2 + (c & 1); GELU(c) leaves the hidden chunk in the same quarter; linear2(c) reads it from
+            // there; linear1(c + 2) then overwrites the quarter (the tensor pipe executes one thread's MMAs in issue order)
+            const long long ffn_t0 = prof ? clock64() : 0, ffn_w0 = t_w, ffn_o0 = t_o;
+            auto ff1 = [&](int c, bool wait_free) {
+              if (wait_free) { owait(B_ACCF + 2 + (c & 1)); tcgen05_fence_after(); }
               for (int kb = 0; kb < 4; ++kb) tile(xs_addr + kb * 1024, (2 + (c & 1)) * 128, idesc128, kb > 0, 4096);
               tcgen05_commit(&bars[B_ACCR + 2 + (c & 1)]);
             };
-            ff1(0); ff1(1);
+            ff1(0, true); ff1(1, true);
             for (int c = 0; c < 8; ++c) {
-              if (c + 2 < 8) ff1(c + 2);                 // before linear2(c): see the producer
-              owait(B_BUFR + (c & 1));
+              owait(B_BUFR + (c & 1));                   // hidden chunk c is in tensor memory
               if (c == 0) { owait(B_ACCF + 0); owait(B_ACCF + 1); }
               tcgen05_fence_after();
               for (int nh = 0; nh < 2; ++nh)
-                for (int kb2 = 0; kb2 < 2; ++kb2) tile(buf_addr + ((c & 1) * 2 + kb2) * KT, nh * 128, idesc128h, c > 0 || kb2 > 0);
-              tcgen05_commit(&bars[B_BUFF + (c & 1)]);
+                for (int kb2 = 0; kb2 < 2; ++kb2)
+                  tile2((uint32_t)((2 + (c & 1)) * 128 + kb2 * 32), nh * 128, idesc128h, c > 0 || kb2 > 0);
+              if (c + 2 < 8) ff1(c + 2, false);
             }
             tcgen05_commit(&bars[B_ACCR + 0]); tcgen05_commit(&bars[B_ACCR + 1]);
+            if (prof) { t_ffn += clock64() - ffn_t0; t_ffn_w += t_w - ffn_w0; t_ffn_o += t_o - ffn_o0; }
             if (l == NL - 1) tcgen05_commit(&bars[B_HGO]);      // every read of BUF by the tensor core is complete
           }
           // ---- pose head: 9 tiles of 128 joint channels, D rotates over the 4 quarters
@@ -405,7 +445,11 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
             tcgen05_commit(&bars[B_ACCR + (t & 3)]);
           }
         }
-      if (prof) { P.prof[PF_TOTAL] = clock64() - t_begin; P.prof[PF_MMA_WAIT_W] = t_w; P.prof[PF_MMA_WAIT_OTHER] = t_o; }
+      if (prof) {
+        P.prof[PF_TOTAL] = clock64() - t_begin; P.prof[PF_MMA_WAIT_W] = t_w; P.prof[PF_MMA_WAIT_OTHER] = t_o;
+        P.prof[PF_MMA_FFN_TOTAL] = t_ffn; P.prof[PF_MMA_FFN_WAIT_W] = t_ffn_w; P.prof[PF_MMA_FFN_WAIT_O] = t_ffn_o;
+        P.prof[PF_MMA_QKV_TOTAL] = t_qkv; P.prof[PF_MMA_QKV_WAIT_W] = t_qkv_w; P.prof[PF_MMA_QKV_WAIT_O] = t_qkv_o;
+      }
     }
   } else if (q4 == 3 && sub == 2) {
     // =================================================== noise pre-draw ===================================================
@@ -430,12 +474,13 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
     // S = Q K^T into columns [0, 96) of the head's TMEM half (the q | k accumulators are already extracted), then O = P V
     // into columns [96, 160).  Operands: canonical no-swizzle core-matrix layouts (AT_*); V is the MN-major B operand.
     if (lane == 0) {
-      Phases ph{0};
+      Phases ph{((1ull << NS2) - 1) << B_W2EMPTY};
       const uint32_t smem_addr0 = smem_u32(smem);
       constexpr uint32_t idesc_s = make_idesc_bf16(128, 96), idesc_o = make_idesc_bf16(128, 64) | (1u << 16);
+      int slot2 = 0;
       for (int clip = blockIdx.x; clip < P.B; clip += gridDim.x)
         for (int k = 0; k < P.n_run; ++k)
-          for (int l = 0; l < NL; ++l)
+          for (int l = 0; l < NL; ++l) {
             for (int h = 0; h < NH; ++h) {
               const uint32_t d0 = tmem + (uint32_t)((h & 1) * 256);
               ph.wait(bars, B_QKR);
@@ -452,7 +497,22 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
                 umma_bf16(d0 + 96, make_nosw_desc(smem_addr0 + AT_P + j * 2 * LBO_P, LBO_P, 128),
                           make_nosw_desc(smem_addr0 + AT_V + j * 2 * LBO_V, LBO_V, 128), idesc_o, j > 0 ? 1u : 0u);
               tcgen05_commit(&bars[B_OR]);
+              ph.wait(bars, B_OR);           // (the next head's operands cannot arrive before the workers have seen this anyway)
             }
+            // the attention operands are dead until the next layer, and BUF once out_proj has read it: they are the ring of this
+            // layer's linear2 weight tiles
+            bool buf_free = false;
+            for (int c = 0; c < 8; ++c)
+              for (int nh = 0; nh < 2; ++nh)
+                for (int kb2 = 0; kb2 < 2; ++kb2) {
+                  if (slot2 >= 2 && !buf_free) { ph.wait(bars, B_BUFF + 0); ph.wait(bars, B_BUFF + 1); buf_free = true; }
+                  ph.wait(bars, B_W2EMPTY + slot2);
+                  mbar_expect_tx(&bars[B_W2FULL + slot2], WSTAGE);
+                  tma_load_2d(smem + w2stage_off(slot2), &tm_w2, &bars[B_W2FULL + slot2], c * 128 + kb2 * 64, l * 256 + nh * 128);
+                  slot2 = (slot2 + 1 == NS2) ? 0 : slot2 + 1;
+                }
+            if (!buf_free) { ph.wait(bars, B_BUFF + 0); ph.wait(bars, B_BUFF + 1); }      // keep the phase bits in step
+          }
     }
   } else {
     // =================================================== workers ===================================================
@@ -806,34 +866,34 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
             lap(PF_W_ATT_MERGE);
           }
           layernorm_epilogue(b1s + 768, lnp, lnp + 256);
-          // ---- FFN: GELU epilogue per 128-unit chunk -> BUF half (c & 1) as the (fp16) A operand of linear2
+          // ---- FFN: GELU epilogue per 128-unit chunk; the fp16 hidden goes back into the chunk's own accumulator quarter
+          // (columns 0..63: column j = units (j, 64 + j)) as the tensor-memory A operand of linear2
           for (int c = 0; c < 8; ++c) {
             const int qd = 2 + (c & 1);
             ph.wait(bars, B_ACCR + qd);
-            ph.wait(bars, B_BUFF + (c & 1));
             lap(PF_W_GELU_WAIT);
             tcgen05_fence_after();
             {
               float va[32];
-              const int cc0 = sub * 32;                  // column inside the chunk
-              tmem_ld32_issue(tlane + qd * 128 + cc0, va);
+              const int cc0 = sub * 16;                  // this thread's units: cc0 .. cc0 + 15 and 64 + cc0 .. 64 + cc0 + 15
+              tmem_ld16_issue(tlane + qd * 128 + cc0, va);
+              tmem_ld16_issue(tlane + qd * 128 + 64 + cc0, va + 16);
               tmem_ld_wait(); tie32(va);
-              tcgen05_fence_before();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(&bars[B_ACCF + qd]);      // accumulator free: values are in registers now
               // GELU in packed fp16 (tanh form on MUFU.TANH, 4 instructions per element): the hidden is stored as fp16, which
               // keeps 3 more mantissa bits than the bf16 it replaces; |half-tanh GELU - exact| rms 5e-4 vs 2e-3 for bf16(exact)
-              const __half2* b1h = reinterpret_cast<const __half2*>(b1s) + ((c * 128 + cc0) >> 1);
+              const __half* b1h = reinterpret_cast<const __half*>(b1s) + c * 128 + cc0;
               uint32_t ha[16];
 #pragma unroll
-              for (int i = 0; i < 16; ++i) ha[i] = gelu_h2(__hadd2(__floats2half2_rn(va[2 * i], va[2 * i + 1]), b1h[i]));
-#pragma unroll
-              for (int i = 0; i < 4; ++i)
-                *reinterpret_cast<uint4*>(BUF + a_off(r, (c & 1) * 128 + cc0 + i * 8)) = make_uint4(ha[4 * i], ha[4 * i + 1], ha[4 * i + 2], ha[4 * i + 3]);
+              for (int i = 0; i < 16; ++i)
+                ha[i] = gelu_h2(__hadd2(__floats2half2_rn(va[i], va[16 + i]), __halves2half2(b1h[i], b1h[64 + i])));
+              tmem_st16(tlane + qd * 128 + cc0, ha);
             }
-            fence_async_smem();
+            tcgen05_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&bars[B_BUFR + (c & 1)]);
+            if (lane == 0) {
+              mbar_arrive(&bars[B_BUFR + (c & 1)]);
+              if (c >= 6) mbar_arrive(&bars[B_ACCF + qd]);      // the quarter's next user (in_proj of the next layer / the pose head) waits for this
+            }
             lap(PF_W_GELU);
           }
           layernorm_epilogue(b1s + 1024, lnp + 512, lnp + 768);
@@ -887,7 +947,7 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
         if (lane == 0) { mbar_arrive(&bars[B_XAR]); if (nz) mbar_arrive(&bars[B_ZF]); }
       }
     }
-    if constexpr (PROF) { if (prof) for (int i = PF_W_STAGE; i < PF_COUNT; ++i) P.prof[i] = pf[i]; }
+    if constexpr (PROF) { if (prof) for (int i = PF_W_STAGE; i <= PF_W_ATT_MERGE; ++i) P.prof[i] = pf[i]; }
   }
   tcgen05_fence_before();
   __syncthreads();

@@ -67,7 +67,7 @@ static int clip_setup(dsg_engine* e) {
         TRY(pack_w(w[L_INPROJ_W] + (size_t)(part * D + h * HD) * D, base + (size_t)(R_QKV + h * 192 + part * 64) * D, 64, D, D, 64, D));
     TRY(pack_w(w[L_OUTPROJ_W], base + (size_t)R_WO * D, D, D, D, D, D));
     TRY(pack_w(w[L_FF1_W], base + (size_t)R_W1 * D, F, D, D, F, D));
-    pack_weight_f16_kernel<<<296, 256>>>(w[L_FF2_W], reinterpret_cast<__half*>(t->wK1024) + (size_t)l * D * F, D, F, F, D, F);   // fp16 slab
+    pack_w2_perm_kernel<<<296, 256>>>(w[L_FF2_W], reinterpret_cast<__half*>(t->wK1024) + (size_t)l * D * F, D, F);   // fp16 slab, hidden-in-TMEM K order
     CUDA_TRY(cudaGetLastError());
     float* p = lp.data() + (size_t)l * P_SIZE;
     CUDA_TRY(fetch(w[L_INPROJ_B], tmp.data(), 3 * D));

@@ -23,6 +23,17 @@ static __global__ void __launch_bounds__(256) pack_weight_f16_kernel(const float
   }
 }
 
+// linear2 weights of the clip kernel: fp16 [rows, cols] with the K (column) order permuted inside every 128-column chunk to
+// the order in which the GELU epilogue leaves the hidden units in tensor memory: K position 2j <- unit j, 2j + 1 <- unit 64 + j.
+static __global__ void __launch_bounds__(256) pack_w2_perm_kernel(const float* __restrict__ src, __half* __restrict__ dst, int rows, int cols) {
+  const long long total = (long long)rows * cols;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(e / cols), c = (int)(e - (long long)r * cols);
+    const int p = c & 127, unit = (p & 1) ? 64 + (p >> 1) : (p >> 1);
+    dst[e] = __float2half_rn(src[(long long)r * cols + (c & ~127) + unit]);
+  }
+}
+
 // x fp32 [B, J, T]  ->  xb bf16 [B, S, Jpad] rows 1..T (row 0 and the pad columns stay zero): the K-major A
 // operand of the input GEMM.  32x32 tile transpose through shared memory; both sides coalesced.
 static __global__ void __launch_bounds__(256) pack_x_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ xb,

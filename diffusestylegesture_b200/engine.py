@@ -259,7 +259,9 @@ class Engine:
         """Cycle counters of the persistent clip kernel's CTA 0 (set DSG_CLIP_PROF=1 before the loop call)."""
         names = ["total", "mma_wait_weights", "mma_wait_other", "producer_wait_empty", "w_stage_x", "w_in_wait", "w_in_epilogue",
                  "w_local_attention", "w_qkv_wait", "w_extract_attention", "w_ln_wait", "w_layernorm", "w_gelu_wait", "w_gelu",
-                 "w_head_wait", "w_head_posterior", "w_noise_wait", "w_att_extract", "w_att_sync1", "w_att_mma", "w_att_merge"]
+                 "w_head_wait", "w_head_posterior", "w_noise_wait", "w_att_extract", "w_att_sync1", "w_att_mma", "w_att_merge",
+                 "mma_ffn_total", "mma_ffn_wait_weights", "mma_ffn_wait_workers", "mma_qkv_total", "mma_qkv_wait_weights",
+                 "mma_qkv_wait_workers"]
         out = torch.empty(32, dtype=torch.float32)
         r = self.lib.dsg_debug_read(self.h, b"clipprof", 1, _ptr(out), 32)
         if r < 0:
