@@ -124,6 +124,16 @@ DSG_DEVINL void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32
       "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
       "}\n" ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// One lane of a converged warp (the same lane every time on this hardware: CUTLASS relies on it for MMA + commit pairs).
+// The issuer roles run warp-converged with warp-uniform operands and elect only the tcgen05 / TMA instruction itself: a role
+// that lives inside `if (lane == 0)` is divergent code to the compiler, which then wraps every UTCHMMA in a per-lane
+// R2UR / ELECT / BRA.U.ANY loop (~20 dependent instructions per MMA: the MMA thread, not the tensor pipe, was the limit).
+DSG_DEVINL bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(pred));
+  return pred != 0;
+}
+DSG_DEVINL uint32_t uniform_u32(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
 DSG_DEVINL void tie4(float* v) { asm volatile("" : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]) :: "memory"); }
 DSG_DEVINL void ldsm_x2(uint32_t& r0, uint32_t& r1, const void* p) {
   const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
@@ -232,7 +242,7 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + B_COUNT);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = (int)uniform_u32(threadIdx.x >> 5), lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < NS; ++i) { mbar_init(&bars[B_WFULL + i], 1); mbar_init(&bars[B_WEMPTY + i], 1); }
@@ -265,15 +275,15 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
-  const uint32_t tmem = *tmem_slot;
-  const int draw0 = P.lp->k;                               // loop iteration of this launch's first step (dump_steps cuts the loop)
-  const int first_index = P.lp->first_index - draw0;
+  const uint32_t tmem = uniform_u32(*tmem_slot);           // (warp-uniform for the compiler: see elect_one)
+  const int draw0 = (int)uniform_u32((uint32_t)P.lp->k);   // loop iteration of this launch's first step (dump_steps cuts the loop)
+  const int first_index = (int)uniform_u32((uint32_t)P.lp->first_index) - draw0;
   const uint32_t key0 = P.lp->key0, key1 = P.lp->key1, segment = P.lp->segment;
 
   const int q4 = warp & 3, sub = warp >> 2;
   if (q4 == 3 && sub == 0) {
     // =================================================== TMA weight producer ===================================================
-    if (lane == 0) {
+    {                                               // warp-converged, elected issue (see elect_one)
       Phases ph{(((1ull << NS) - 1) << B_WEMPTY) | (0xFull << B_AEMPTY) | (0xFull << B_HEMPTY)};     // "empty" barriers start free
       int slot = 0;
       long long t_wait = 0;
@@ -282,8 +292,11 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
         const long long c0 = prof ? clock64() : 0;
         ph.wait(bars, B_WEMPTY + slot);
         if (prof) t_wait += clock64() - c0;
-        mbar_expect_tx(&bars[B_WFULL + slot], bytes);
-        tma_load_2d(smem + wstage_off(slot), m, &bars[B_WFULL + slot], kcol, row);
+        if (elect_one()) {
+          mbar_expect_tx(&bars[B_WFULL + slot], bytes);
+          tma_load_2d(smem + wstage_off(slot), m, &bars[B_WFULL + slot], kcol, row);
+        }
+        __syncwarp();
         slot = (slot + 1 == NS) ? 0 : slot + 1;
       };
       bool first = true;
@@ -299,8 +312,11 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
           for (int kb = 0; kb < JPAD / 64; ++kb) {
             const int sl = kb & 3;
             ph.wait(bars, B_AEMPTY + sl);
-            mbar_expect_tx(&bars[B_AFULL + sl], KT);
-            bulk_load(smem + OFF_BUF + sl * KT, xa + (long long)kb * KT, KT, &bars[B_AFULL + sl]);
+            if (elect_one()) {
+              mbar_expect_tx(&bars[B_AFULL + sl], KT);
+              bulk_load(smem + OFF_BUF + sl * KT, xa + (long long)kb * KT, KT, &bars[B_AFULL + sl]);
+            }
+            __syncwarp();
             for (int nh = 0; nh < 2; ++nh) load(&tm_in, nh * 128, kb * 64, WSTAGE);
           }
           for (int l = 0; l < NL; ++l) {
@@ -324,9 +340,12 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
             const int sl = c & 3, j0 = c * HCH;
             const uint32_t bytes = (uint32_t)((J - j0 < HCH ? J - j0 : HCH) * T * 4);
             ph.wait(bars, B_HEMPTY + sl);
-            mbar_expect_tx(&bars[B_HFULL + sl], nz ? 2 * bytes : bytes);
-            bulk_load(smem + hslot_x(sl), xc + (long long)j0 * T, bytes, &bars[B_HFULL + sl]);
-            if (nz) bulk_load(smem + hslot_z(sl), zc + (long long)j0 * T, bytes, &bars[B_HFULL + sl]);
+            if (elect_one()) {
+              mbar_expect_tx(&bars[B_HFULL + sl], nz ? 2 * bytes : bytes);
+              bulk_load(smem + hslot_x(sl), xc + (long long)j0 * T, bytes, &bars[B_HFULL + sl]);
+              if (nz) bulk_load(smem + hslot_z(sl), zc + (long long)j0 * T, bytes, &bars[B_HFULL + sl]);
+            }
+            __syncwarp();
           };
           for (int c = 0; c < NHS; ++c) hload(c);
           for (int t = 1; t < JPAD / 128; ++t) {
@@ -334,11 +353,11 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
             for (int c = 4 * t; c < 4 * t + 4; ++c) hload(c);
           }
         }
-      if (prof) P.prof[PF_PROD_WAIT_EMPTY] = t_wait;
+      if (prof && lane == 0) P.prof[PF_PROD_WAIT_EMPTY] = t_wait;
     }
   } else if (q4 == 3 && sub == 1) {
     // =================================================== MMA issuer ===================================================
-    if (lane == 0) {
+    {                                               // the whole warp runs the role converged; one elected lane issues
       Phases ph{(0xFull << B_ACCF)};               // accumulators start free
       int slot = 0;
       const uint32_t xs_addr = smem_u32(smem + OFF_XS), buf_addr = smem_u32(smem + OFF_BUF), smem_addr0 = smem_u32(smem);
@@ -353,10 +372,13 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
         if (prof) t_w += clock64() - c0;
         tcgen05_fence_after();
         const uint32_t b_tile = smem_addr0 + wstage_off(slot);
+        if (elect_one()) {
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk)
-          umma_bf16(tmem + d_col, make_sw128_desc_sbo(a_tile + kk * 32, a_sbo), make_sw128_desc(b_tile + kk * 32), idesc, (acc_first || kk > 0) ? 1u : 0u);
-        tcgen05_commit(&bars[B_WEMPTY + slot]);
+          for (int kk = 0; kk < 4; ++kk)
+            umma_bf16(tmem + d_col, make_sw128_desc_sbo(a_tile + kk * 32, a_sbo), make_sw128_desc(b_tile + kk * 32), idesc, (acc_first || kk > 0) ? 1u : 0u);
+          tcgen05_commit(&bars[B_WEMPTY + slot]);
+        }
+        __syncwarp();
         slot = (slot + 1 == NS) ? 0 : slot + 1;
       };
       int slot2 = 0;
@@ -367,10 +389,13 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
         if (prof) t_w += clock64() - c0;
         tcgen05_fence_after();
         const uint32_t b_tile = smem_addr0 + w2stage_off(slot2);
+        if (elect_one()) {
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk)
-          umma_ts(tmem + d_col, tmem + a_tmem + kk * 8, make_sw128_desc(b_tile + kk * 32), idesc, (acc_first || kk > 0) ? 1u : 0u);
-        tcgen05_commit(&bars[B_W2EMPTY + slot2]);
+          for (int kk = 0; kk < 4; ++kk)
+            umma_ts(tmem + d_col, tmem + a_tmem + kk * 8, make_sw128_desc(b_tile + kk * 32), idesc, (acc_first || kk > 0) ? 1u : 0u);
+          tcgen05_commit(&bars[B_W2EMPTY + slot2]);
+        }
+        __syncwarp();
         slot2 = (slot2 + 1 == NS2) ? 0 : slot2 + 1;
       };
       auto owait = [&](int id) { const long long c0 = prof ? clock64() : 0; ph.wait(bars, id); if (prof) t_o += clock64() - c0; };
@@ -382,9 +407,9 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
             owait(B_AFULL + (kb & 3));
             tcgen05_fence_after();
             for (int nh = 0; nh < 2; ++nh) tile(buf_addr + (kb & 3) * KT, nh * 128, idesc128, kb > 0);
-            tcgen05_commit(&bars[B_AEMPTY + (kb & 3)]);
+            if (elect_one()) { tcgen05_commit(&bars[B_AEMPTY + (kb & 3)]); }
           }
-          tcgen05_commit(&bars[B_ACCR + 0]); tcgen05_commit(&bars[B_ACCR + 1]);
+          if (elect_one()) { tcgen05_commit(&bars[B_ACCR + 0]); tcgen05_commit(&bars[B_ACCR + 1]); }
           for (int l = 0; l < NL; ++l) {
             // ---- in_proj, one head at a time into alternating TMEM halves: q | k | v = 3 x 64 columns
             owait(B_XSR);
@@ -396,7 +421,7 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
               tcgen05_fence_after();
               for (int kb = 0; kb < 4; ++kb) tile(xs_addr + kb * 1024, hb * 256, idesc128, kb > 0, 4096);            // q | k
               for (int kb = 0; kb < 4; ++kb) tile(xs_addr + kb * 1024, hb * 256 + 128, idesc64, kb > 0, 4096);      // v
-              tcgen05_commit(&bars[B_ACCR + 2 * hb]); tcgen05_commit(&bars[B_ACCR + 2 * hb + 1]);
+              if (elect_one()) { tcgen05_commit(&bars[B_ACCR + 2 * hb]); tcgen05_commit(&bars[B_ACCR + 2 * hb + 1]); }
             };
             // (S = Q K^T and O = P V of every head are issued by the attention issuer, warp 15; a head's TMEM half comes back
             //  after its O epilogue, which is what in_proj(h + 2) waits for)
@@ -408,8 +433,8 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
             tcgen05_fence_after();
             for (int nh = 0; nh < 2; ++nh)
               for (int kb = 0; kb < 4; ++kb) tile(buf_addr + kb * KT, nh * 128, idesc128, kb > 0);
-            tcgen05_commit(&bars[B_ACCR + 0]); tcgen05_commit(&bars[B_ACCR + 1]);
-            tcgen05_commit(&bars[B_BUFF + 0]); tcgen05_commit(&bars[B_BUFF + 1]);
+            if (elect_one()) { tcgen05_commit(&bars[B_ACCR + 0]); tcgen05_commit(&bars[B_ACCR + 1]); }
+            if (elect_one()) { tcgen05_commit(&bars[B_BUFF + 0]); tcgen05_commit(&bars[B_BUFF + 1]); }
             // ---- FFN: linear1 in 8 chunks of 128 hidden units (D = Q2 / Q3 alternating), linear2 accumulates into Q0|Q1
             owait(B_XSR);
             tcgen05_fence_after();
@@ -419,7 +444,7 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
             auto ff1 = [&](int c, bool wait_free) {
               if (wait_free) { owait(B_ACCF + 2 + (c & 1)); tcgen05_fence_after(); }
               for (int kb = 0; kb < 4; ++kb) tile(xs_addr + kb * 1024, (2 + (c & 1)) * 128, idesc128, kb > 0, 4096);
-              tcgen05_commit(&bars[B_ACCR + 2 + (c & 1)]);
+              if (elect_one()) { tcgen05_commit(&bars[B_ACCR + 2 + (c & 1)]); }
             };
             ff1(0, true); ff1(1, true);
             for (int c = 0; c < 8; ++c) {
@@ -431,9 +456,9 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
                   tile2((uint32_t)((2 + (c & 1)) * 128 + kb2 * 32), nh * 128, idesc128h, c > 0 || kb2 > 0);
               if (c + 2 < 8) ff1(c + 2, false);
             }
-            tcgen05_commit(&bars[B_ACCR + 0]); tcgen05_commit(&bars[B_ACCR + 1]);
+            if (elect_one()) { tcgen05_commit(&bars[B_ACCR + 0]); tcgen05_commit(&bars[B_ACCR + 1]); }
             if (prof) { t_ffn += clock64() - ffn_t0; t_ffn_w += t_w - ffn_w0; t_ffn_o += t_o - ffn_o0; }
-            if (l == NL - 1) tcgen05_commit(&bars[B_HGO]);      // every read of BUF by the tensor core is complete
+            if (l == NL - 1 && elect_one()) tcgen05_commit(&bars[B_HGO]);      // every read of BUF by the tensor core is complete
           }
           // ---- pose head: 9 tiles of 128 joint channels, D rotates over the 4 quarters
           owait(B_XSR);
@@ -442,10 +467,10 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
             owait(B_ACCF + (t & 3));
             tcgen05_fence_after();
             for (int kb = 0; kb < 4; ++kb) tile(xs_addr + kb * 1024, (t & 3) * 128, idesc128, kb > 0, 4096);
-            tcgen05_commit(&bars[B_ACCR + (t & 3)]);
+            if (elect_one()) { tcgen05_commit(&bars[B_ACCR + (t & 3)]); }
           }
         }
-      if (prof) {
+      if (prof && lane == 0) {
         P.prof[PF_TOTAL] = clock64() - t_begin; P.prof[PF_MMA_WAIT_W] = t_w; P.prof[PF_MMA_WAIT_OTHER] = t_o;
         P.prof[PF_MMA_FFN_TOTAL] = t_ffn; P.prof[PF_MMA_FFN_WAIT_W] = t_ffn_w; P.prof[PF_MMA_FFN_WAIT_O] = t_ffn_o;
         P.prof[PF_MMA_QKV_TOTAL] = t_qkv; P.prof[PF_MMA_QKV_WAIT_W] = t_qkv_w; P.prof[PF_MMA_QKV_WAIT_O] = t_qkv_o;
@@ -473,7 +498,7 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
     // Global attention of every head on the tensor core, from its own thread so that it never queues behind a weight tile:
     // S = Q K^T into columns [0, 96) of the head's TMEM half (the q | k accumulators are already extracted), then O = P V
     // into columns [96, 160).  Operands: canonical no-swizzle core-matrix layouts (AT_*); V is the MN-major B operand.
-    if (lane == 0) {
+    {                                               // warp-converged, elected issue (see elect_one)
       Phases ph{((1ull << NS2) - 1) << B_W2EMPTY};
       const uint32_t smem_addr0 = smem_u32(smem);
       constexpr uint32_t idesc_s = make_idesc_bf16(128, 96), idesc_o = make_idesc_bf16(128, 64) | (1u << 16);
@@ -485,18 +510,24 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
               const uint32_t d0 = tmem + (uint32_t)((h & 1) * 256);
               ph.wait(bars, B_QKR);
               tcgen05_fence_after();
+              if (elect_one()) {
 #pragma unroll
-              for (int j = 0; j < 4; ++j)
-                umma_bf16(d0, make_nosw_desc(smem_addr0 + AT_Q + j * 2 * LBO_Q, LBO_Q, 128),
-                          make_nosw_desc(smem_addr0 + AT_K + j * 2 * LBO_K, LBO_K, 128), idesc_s, j > 0 ? 1u : 0u);
-              tcgen05_commit(&bars[B_SR]);
+                for (int j = 0; j < 4; ++j)
+                  umma_bf16(d0, make_nosw_desc(smem_addr0 + AT_Q + j * 2 * LBO_Q, LBO_Q, 128),
+                            make_nosw_desc(smem_addr0 + AT_K + j * 2 * LBO_K, LBO_K, 128), idesc_s, j > 0 ? 1u : 0u);
+                tcgen05_commit(&bars[B_SR]);
+              }
+              __syncwarp();
               ph.wait(bars, B_PR);
               tcgen05_fence_after();
+              if (elect_one()) {
 #pragma unroll
-              for (int j = 0; j < 6; ++j)
-                umma_bf16(d0 + 96, make_nosw_desc(smem_addr0 + AT_P + j * 2 * LBO_P, LBO_P, 128),
-                          make_nosw_desc(smem_addr0 + AT_V + j * 2 * LBO_V, LBO_V, 128), idesc_o, j > 0 ? 1u : 0u);
-              tcgen05_commit(&bars[B_OR]);
+                for (int j = 0; j < 6; ++j)
+                  umma_bf16(d0 + 96, make_nosw_desc(smem_addr0 + AT_P + j * 2 * LBO_P, LBO_P, 128),
+                            make_nosw_desc(smem_addr0 + AT_V + j * 2 * LBO_V, LBO_V, 128), idesc_o, j > 0 ? 1u : 0u);
+                tcgen05_commit(&bars[B_OR]);
+              }
+              __syncwarp();
               ph.wait(bars, B_OR);           // (the next head's operands cannot arrive before the workers have seen this anyway)
             }
             // the attention operands are dead until the next layer, and BUF once out_proj has read it: they are the ring of this
@@ -507,8 +538,11 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
                 for (int kb2 = 0; kb2 < 2; ++kb2) {
                   if (slot2 >= 2 && !buf_free) { ph.wait(bars, B_BUFF + 0); ph.wait(bars, B_BUFF + 1); buf_free = true; }
                   ph.wait(bars, B_W2EMPTY + slot2);
-                  mbar_expect_tx(&bars[B_W2FULL + slot2], WSTAGE);
-                  tma_load_2d(smem + w2stage_off(slot2), &tm_w2, &bars[B_W2FULL + slot2], c * 128 + kb2 * 64, l * 256 + nh * 128);
+                  if (elect_one()) {
+                    mbar_expect_tx(&bars[B_W2FULL + slot2], WSTAGE);
+                    tma_load_2d(smem + w2stage_off(slot2), &tm_w2, &bars[B_W2FULL + slot2], c * 128 + kb2 * 64, l * 256 + nh * 128);
+                  }
+                  __syncwarp();
                   slot2 = (slot2 + 1 == NS2) ? 0 : slot2 + 1;
                 }
             if (!buf_free) { ph.wait(bars, B_BUFF + 0); ph.wait(bars, B_BUFF + 1); }      // keep the phase bits in step
