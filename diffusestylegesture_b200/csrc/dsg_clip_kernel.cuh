@@ -128,11 +128,7 @@ DSG_DEVINL void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32
 // The issuer roles run warp-converged with warp-uniform operands and elect only the tcgen05 / TMA instruction itself: a role
 // that lives inside `if (lane == 0)` is divergent code to the compiler, which then wraps every UTCHMMA in a per-lane
 // R2UR / ELECT / BRA.U.ANY loop (~20 dependent instructions per MMA: the MMA thread, not the tensor pipe, was the limit).
-DSG_DEVINL bool elect_one() {
-  uint32_t pred;
-  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(pred));
-  return pred != 0;
-}
+DSG_DEVINL bool elect_one() { return elect_one_lane(); }
 DSG_DEVINL uint32_t uniform_u32(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
 DSG_DEVINL void tie4(float* v) { asm volatile("" : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]) :: "memory"); }
 DSG_DEVINL void ldsm_x2(uint32_t& r0, uint32_t& r1, const void* p) {

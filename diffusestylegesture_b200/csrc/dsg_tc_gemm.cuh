@@ -71,6 +71,11 @@ DSG_DEVINL void tma_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* ba
   asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
                ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
+DSG_DEVINL bool elect_one_lane() {            // one lane of a converged warp (the same lane on every call)
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(pred));
+  return pred != 0;
+}
 DSG_DEVINL void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 DSG_DEVINL void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 DSG_DEVINL void tcgen05_commit(uint64_t* bar) {
@@ -214,7 +219,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
   float* red = reinterpret_cast<float*>(smem + SM::RED_OFF);     // [2 halves][128 rows][2] LayerNorm partials
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;     // warp-uniform for the compiler
   const int zdiv = ep.z_div > 0 ? ep.z_div : 1;
   const int zb = (int)blockIdx.z / zdiv, zg = (int)blockIdx.z - zb * zdiv;
   const int m0 = blockIdx.x * BM, n0 = (blockIdx.y + zg) * BN;
@@ -240,23 +245,30 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t tmem_base = *tmem_slot;
   constexpr int NSPLIT = TcTile<BN>::NSPLIT, NSUB = TcTile<BN>::NSUB;
 
-  if (warp == 0 && lane == 0) {
+  // Both roles run warp-converged with warp-uniform operands; only the TMA / tcgen05 instruction itself is issued by one
+  // elected lane.  (Inside `if (lane == 0)` the compiler treats the operands as divergent and wraps every UTMALDG / UTCHMMA
+  // in an R2UR / ELECT / BRA.U.ANY loop of ~20 dependent instructions: the issuing thread becomes the limit.)
+  if (warp == 0) {
     // ===== TMA producer =====
     for (int kb = 0; kb < num_kb; ++kb) {
       const int s = kb % STAGES;
       const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
       mbar_wait(&empty_bar[s], ph ^ 1u);
-      mbar_expect_tx(&full_bar[s], SM::STAGE_BYTES);
       uint8_t* a_dst = smem + s * SM::STAGE_BYTES;
-      if (ep.rows_per_z > 0) tma_load_3d(a_dst, &tmA, &full_bar[s], kb * BK, m0, (int)blockIdx.z);
-      else tma_load_2d(a_dst, &tmA, &full_bar[s], kb * BK, m0);
+      if (elect_one_lane()) {
+        mbar_expect_tx(&full_bar[s], SM::STAGE_BYTES);
+        if (ep.rows_per_z > 0) tma_load_3d(a_dst, &tmA, &full_bar[s], kb * BK, m0, (int)blockIdx.z);
+        else tma_load_2d(a_dst, &tmA, &full_bar[s], kb * BK, m0);
 #pragma unroll
-      for (int i = 0; i < NSPLIT; ++i)
-        tma_load_2d(a_dst + SM::A_BYTES + i * NSUB * 128, &tmB, &full_bar[s], kb * BK, n0 + i * NSUB);
+        for (int i = 0; i < NSPLIT; ++i)
+          tma_load_2d(a_dst + SM::A_BYTES + i * NSUB * 128, &tmB, &full_bar[s], kb * BK, n0 + i * NSUB);
+      }
+      __syncwarp();
     }
-  } else if (warp == 1 && lane == 0) {
+  } else if (warp == 1) {
     // ===== MMA issuer =====
     constexpr uint32_t idesc = make_idesc_bf16(BM, NSUB);
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
     for (int kb = 0; kb < num_kb; ++kb) {
       const int s = kb % STAGES;
       const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
@@ -264,16 +276,19 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tcgen05_fence_after();
       const uint32_t a_addr = smem_u32(smem + s * SM::STAGE_BYTES);
       const uint32_t b_addr = a_addr + SM::A_BYTES;
+      if (elect_one_lane()) {
 #pragma unroll
-      for (int k = 0; k < BK / UMMA_K; ++k) {
-        const uint64_t adesc = make_sw128_desc(a_addr + k * UMMA_K * 2);
+        for (int k = 0; k < BK / UMMA_K; ++k) {
+          const uint64_t adesc = make_sw128_desc(a_addr + k * UMMA_K * 2);
 #pragma unroll
-        for (int i = 0; i < NSPLIT; ++i)
-          umma_bf16(tmem_base + i * NSUB, adesc, make_sw128_desc(b_addr + i * NSUB * 128 + k * UMMA_K * 2), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          for (int i = 0; i < NSPLIT; ++i)
+            umma_bf16(tmem_u + i * NSUB, adesc, make_sw128_desc(b_addr + i * NSUB * 128 + k * UMMA_K * 2), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+        }
+        tcgen05_commit(&empty_bar[s]);            // frees the smem stage when these MMAs retire
       }
-      tcgen05_commit(&empty_bar[s]);            // frees the smem stage when these MMAs retire
+      __syncwarp();
     }
-    tcgen05_commit(tmem_full);                  // accumulator complete
+    if (elect_one_lane()) tcgen05_commit(tmem_full);                  // accumulator complete
   }
   __syncwarp();
 
