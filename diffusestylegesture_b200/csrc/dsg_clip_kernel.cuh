@@ -130,6 +130,8 @@ DSG_DEVINL void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32
 // R2UR / ELECT / BRA.U.ANY loop (~20 dependent instructions per MMA: the MMA thread, not the tensor pipe, was the limit).
 DSG_DEVINL bool elect_one() { return elect_one_lane(); }
 DSG_DEVINL uint32_t uniform_u32(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
+// 2^x on MUFU.EX2 directly (ex2.approx.ftz: 2 ulp; exp2f() adds a subnormal-range rescale = 4 more instructions per element)
+DSG_DEVINL float ex2_fast(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 DSG_DEVINL void tie4(float* v) { asm volatile("" : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]) :: "memory"); }
 DSG_DEVINL void ldsm_x2(uint32_t& r0, uint32_t& r1, const void* p) {
   const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
@@ -720,8 +722,8 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
           float s0 = 0.f, s1 = 0.f;
 #pragma unroll
           for (int nt = 0; nt < 3; ++nt) {
-            sc[nt][0] = exp2f((sc[nt][0] - mx0) * sl2); sc[nt][1] = exp2f((sc[nt][1] - mx0) * sl2);
-            sc[nt][2] = exp2f((sc[nt][2] - mx1) * sl2); sc[nt][3] = exp2f((sc[nt][3] - mx1) * sl2);
+            sc[nt][0] = ex2_fast((sc[nt][0] - mx0) * sl2); sc[nt][1] = ex2_fast((sc[nt][1] - mx0) * sl2);
+            sc[nt][2] = ex2_fast((sc[nt][2] - mx1) * sl2); sc[nt][3] = ex2_fast((sc[nt][3] - mx1) * sl2);
             s0 += sc[nt][0] + sc[nt][1]; s1 += sc[nt][2] + sc[nt][3];
           }
           s0 += __shfl_xor_sync(0xffffffffu, s0, 1); s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
@@ -858,8 +860,9 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
               mx = fmaxf(fmaxf(red_s[r], red_s[96 + r]), fmaxf(red_s[192 + r], red_s[288 + r]));
               const float sl2 = 1.4426950408889634f * 0.125f;
               float sum = 0.f;
+              const float mxs = mx * sl2;
 #pragma unroll
-              for (int i = 0; i < 24; ++i) { sc[i] = exp2f((sc[i] - mx) * sl2); sum += sc[i]; }
+              for (int i = 0; i < 24; ++i) { sc[i] = ex2_fast(fmaf(sc[i], sl2, -mxs)); sum += sc[i]; }
               red_q[sub * 96 + r] = sum;
               uint8_t* pd = smem + AT_P + (sub * 3) * LBO_P + (r >> 3) * 128 + (r & 7) * 16;
               *reinterpret_cast<uint4*>(pd) = pack8(sc);
