@@ -239,21 +239,33 @@ def inference(args, wavlm_model, audio, sample_fn, model, n_frames=0, smoothing=
 
 
 def load_wav_16k(path):
-    """Mono 16 kHz float32 waveform (stands in for librosa.load(path, sr=16000), sample.py:346)."""
-    import wave
-    with wave.open(path, 'rb') as w:
-        sr, n, ch, width = w.getframerate(), w.getnframes(), w.getnchannels(), w.getsampwidth()
-        raw = w.readframes(n)
-    if width != 2:
-        raise NotImplementedError("only 16-bit PCM wav files are supported")
-    x = np.frombuffer(raw, dtype='<i2').astype(np.float32) / 32768.0
-    if ch > 1:
-        x = x.reshape(-1, ch).mean(axis=1)
+    """Mono 16 kHz float32 waveform (stands in for librosa.load(path, sr=16000), sample.py:346): PCM 8 / 16 / 24 / 32 bit and
+    IEEE-float wav files, channels averaged, integer samples scaled by 2^-(bits-1) as libsndfile does.  Files at 16 kHz (the
+    ZEGGS data) come out exactly as librosa returns them; other rates are resampled with a polyphase FIR
+    (scipy.signal.resample_poly) — librosa's default resampler (soxr / kaiser_best, version dependent) differs from it by
+    ~1e-3 of full scale."""
+    from scipy.io import wavfile
+    try:
+        sr, d = wavfile.read(path)
+    except ValueError as ex:
+        raise NotImplementedError(f"{path}: unsupported wav encoding ({ex})") from ex
+    if d.dtype == np.uint8:
+        x = (d.astype(np.float32) - 128.0) / 128.0
+    elif d.dtype == np.int16:
+        x = d.astype(np.float32) / 32768.0
+    elif d.dtype == np.int32:                     # 32-bit PCM, and 24-bit PCM (scipy left-justifies it in int32)
+        x = (d.astype(np.float64) / 2147483648.0).astype(np.float32)
+    elif d.dtype in (np.float32, np.float64):
+        x = d.astype(np.float32)
+    else:
+        raise NotImplementedError(f"{path}: sample type {d.dtype}")
+    if x.ndim > 1:
+        x = x.mean(axis=1)
     if sr != 16000:
         from scipy.signal import resample_poly
-        gdiv = math.gcd(sr, 16000)
-        x = resample_poly(x, 16000 // gdiv, sr // gdiv).astype(np.float32)
-    return x, 16000
+        gdiv = math.gcd(int(sr), 16000)
+        x = resample_poly(x, 16000 // gdiv, int(sr) // gdiv).astype(np.float32)
+    return np.ascontiguousarray(x, dtype=np.float32), 16000
 
 
 def main(args, save_dir, model_path, audio_path=None, mfcc_path=None, audiowavlm_path=None, max_len=0, wavlm_model=None,

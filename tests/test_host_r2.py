@@ -1,0 +1,147 @@
+"""CPU: round-2 host logic — BEAT-TWH driver helpers, BVH / feature tails against reference golden, wav loading."""
+import os
+import wave
+
+import numpy as np
+import pytest
+import torch
+
+from diffusestylegesture_b200 import sample as S
+from diffusestylegesture_b200 import sample_beat_twh as SB
+from diffusestylegesture_b200 import process_beat_twh_bvh as PB
+
+
+def test_beat_presets_and_cli():
+    """BEAT-TWH-main/mydiffusion_beat_twh/sample.py:275-321: flags, cond_mode from `name`, dataset / version presets."""
+    c = SB.parse_cli(["--dataset", "BEAT", "--tst_prefix", "2_scott_0_1_1", "10_kieks_0_95_95", "--skip_timesteps", "3"])
+    assert (c.njoints, c.motion_dim, c.latent_dim, c.style_dim, c.audio_feature_dim) == (2052, 684, 384, 2, 1434)
+    assert c.cond_mode == 'cross_local_attention4_style1_sample' and c.tst_prefix == ["2_scott_0_1_1", "10_kieks_0_95_95"]
+    assert c.skip_timesteps == 3 and c.n_poses == 150 and c.n_seed == 30
+    t = SB.parse_cli(["--dataset", "TWH"])
+    assert (t.njoints, t.latent_dim, t.audio_feat_dim_latent, t.style_dim, t.audio_feature_dim) == (2232, 512, 128, 17, 1435)
+    cfg = SB.Config(dict(c, name="DiffuseStyleGesture++"))
+    assert SB.resolve_presets(cfg).cond_mode == 'cross_local_attention5_style1_sample'
+    with pytest.raises(NotImplementedError):
+        SB.resolve_presets(SB.Config(dict(c, dataset="ZEGGS")))
+    m, _ = SB.create_model_and_diffusion(c)
+    assert m.geometry.latent_dim == 384 and m.geometry.audio_frames == 120 and m.geometry.local_window == 15
+
+
+def test_beat_subdivision_and_seed():
+    """sample.py:54-62 (ceil subdivision, zero-padded) and :129-136 (velocity / acceleration seed)."""
+    assert SB.plan_subdivision(900, 150, 30) == (8, 960)
+    assert SB.plan_subdivision(960, 150, 30) == (8, 960)
+    assert SB.plan_subdivision(961, 150, 30) == (9, 1080)
+    assert SB.plan_subdivision(50, 150, 30) == (1, 120)
+    rng = np.random.default_rng(0)
+    g = rng.normal(size=(32, 5))
+    mean, std = rng.normal(size=5), rng.uniform(0.5, 2, size=5)
+    s = SB.seed_from_gesture(g, mean, std)
+    assert tuple(s.shape) == (1, 15, 1, 30)
+    n = (g - mean) / std
+    want = np.concatenate((n[2:], (n[1:] - n[:-1])[1:], n[2:] - 2 * n[1:-1] + n[:-2]), axis=1)
+    assert np.allclose(s[0, :, 0, :].numpy().T, want, atol=1e-6)
+    mean_b, std_b = SB.load_stats('BEAT')
+    mean_t, std_t = SB.load_stats('TWH')
+    assert mean_b.shape == std_b.shape == (684,) and mean_t.shape == (744,) and float(std_b.min()) > 0
+
+
+def test_bvh_tail_numeric_part_matches_reference(gold_dir, tmp_path):
+    """pose2bvh_bugfix / TWH pose2bvh (process_BEAT_bvh.py:108-131, process_TWH_bvh.py:201-226): the array the reference hands
+    to the pymo pipeline, and the call protocol with a stand-in pipeline / writer (the pickled pipelines need pymo)."""
+    gold = np.load(os.path.join(gold_dir, "bvh_tail_beat_twh.npz"))
+    e = PB.beat_euler(gold["beat_poses"])
+    d = np.abs((e - gold["beat_euler"] + 180.0) % 360.0 - 180.0).max()
+    assert d < 1e-6, d
+    t = PB.twh_pos_euler(gold["twh_gesture"])
+    assert np.abs((t - gold["twh_pos_euler"] + 180.0) % 360.0 - 180.0).max() < 1e-6
+    seen = {}
+
+    class Pipe:
+        def inverse_transform(self, xs):
+            seen["x"] = xs[0]
+            return ["BVHDATA"]
+
+    class Writer:
+        def write(self, data, f, framerate=None):
+            f.write(f"{data} {framerate}\n")
+    p = PB.pose2bvh_bugfix(str(tmp_path), "clip", gold["beat_poses"], pipeline=Pipe(), writer=Writer())
+    assert os.path.basename(p) == "clip_generated.bvh" and open(p).read() == "BVHDATA None\n" and np.allclose(seen["x"], e)
+    p = PB.pose2bvh_twh(gold["twh_gesture"], str(tmp_path), "clip", pipeline_path=Pipe(), writer=Writer())
+    assert os.path.basename(p) == "clip.bvh" and open(p).read() == "BVHDATA 30\n"
+    with pytest.raises(PB.PipelineUnavailable):
+        PB.pose2bvh_bugfix(str(tmp_path), "clip", gold["beat_poses"], pipeline=str(tmp_path / "missing.sav"))
+
+
+def test_load_tsv_and_metadata_match_reference(gold_dir, tmp_path):
+    gold = np.load(os.path.join(gold_dir, "bvh_tail_beat_twh.npz"))
+    w2v = {str(w): v for w, v in zip(gold["tsv_words"], gold["tsv_vecs"])}
+    tsv = tmp_path / "t.tsv"
+    tsv.write_text("0.10\t0.50\thello\n0.50\t1.20\tbig world\n1.30\t1.60\t#laugh#\n2.00\t2.40\tunknownword,\n")
+    assert np.array_equal(PB.load_tsv(str(tsv), w2v, 90), gold["tsv_feats"])
+    vec = tmp_path / "v.vec"
+    vec.write_text("2 3\nhello 1 2 3\nworld 4 5 6.5\n")
+    wv = PB.load_wordvectors(str(vec))
+    assert list(wv) == ["hello", "world"] and np.allclose(wv["world"], [4, 5, 6.5])
+    meta = tmp_path / "metadata.csv"
+    meta.write_text("prefix,main_id,main_finger,iloc_id,iloc_finger\nval_001,3,finger_incl,7,finger_excl\nval_002,1,finger_excl,3,finger_incl\n")
+    n, by_name, by_index = PB.load_metadata(str(meta), "main-agent")
+    assert n == 2 and by_name["val_001_main-agent"] == (True, 2) and by_index[1] == (False, 0)
+    n, by_name, _ = PB.load_metadata(str(meta), "interloctr")
+    assert by_name["val_002_interloctr"] == (True, 2)
+
+
+def _write_wav(path, x, sr, width):
+    with wave.open(str(path), "wb") as w:
+        w.setnchannels(1 if x.ndim == 1 else x.shape[1])
+        w.setsampwidth(width)
+        w.setframerate(sr)
+        if width == 2:
+            w.writeframes((np.clip(x, -1, 1) * 32767).astype("<i2").tobytes())
+        else:
+            v = (np.clip(x, -1, 1) * 8388607).astype("<i4")
+            w.writeframes(b"".join(int(s).to_bytes(3, "little", signed=True) for s in v.reshape(-1)))
+
+
+def test_load_wav_16k(tmp_path):
+    """Stands in for librosa.load(path, sr=16000) (sample.py:346): 16 kHz PCM16 exactly int16 / 32768; stereo averaged; 24-bit;
+    24 kHz (the BEAT-TWH tts.wav rate) resampled 3:2 — a 440 Hz tone comes out as the 16 kHz tone."""
+    rng = np.random.default_rng(1)
+    x = (0.4 * rng.standard_normal(16000)).clip(-1, 1)
+    _write_wav(tmp_path / "a.wav", x, 16000, 2)
+    y, sr = S.load_wav_16k(str(tmp_path / "a.wav"))
+    assert sr == 16000 and y.dtype == np.float32 and np.array_equal(y, (np.clip(x, -1, 1) * 32767).astype("<i2").astype(np.float32) / 32768.0)
+    assert S.wav_frames_16k(str(tmp_path / "a.wav")) == 20
+    _write_wav(tmp_path / "s.wav", np.stack([0.5 * x, -0.5 * x + 0.1], axis=1), 16000, 2)
+    assert np.abs(S.load_wav_16k(str(tmp_path / "s.wav"))[0] - 0.05).max() < 1e-4
+    _write_wav(tmp_path / "b24.wav", x, 16000, 3)
+    assert np.abs(S.load_wav_16k(str(tmp_path / "b24.wav"))[0] - x).max() < 1e-6
+    t24 = np.arange(24000 * 2) / 24000.0
+    _write_wav(tmp_path / "t.wav", 0.5 * np.sin(2 * np.pi * 440 * t24), 24000, 2)
+    y, _ = S.load_wav_16k(str(tmp_path / "t.wav"))
+    assert y.shape[0] == 32000 and S.wav_frames_16k(str(tmp_path / "t.wav")) == 40
+    t16 = np.arange(32000) / 16000.0
+    assert np.abs(y[400:-400] - 0.5 * np.sin(2 * np.pi * 440 * t16)[400:-400]).max() < 2e-3
+    for p in ("/root/reference/main/mydiffusion_zeggs/015_Happy_4_x_1_0.wav", "/root/reference/BEAT-TWH-main/data/tts.wav"):
+        if os.path.exists(p):                     # the reference's own clips (authoring container only)
+            y, sr = S.load_wav_16k(p)
+            assert sr == 16000 and y.ndim == 1 and np.isfinite(y).all() and 0.1 < np.abs(y).max() <= 1.0
+            assert S.wav_frames_16k(p) == y.shape[0] * 20 // 16000
+
+
+def test_sampler_option_surface():
+    """Options added in round 2 keep the reference's argument names and error behaviour (no GPU needed for the checks)."""
+    from diffusestylegesture_b200.model_util import create_gaussian_diffusion
+    d = create_gaussian_diffusion([50])
+    coef, qs, tmap = d.engine_tables("plms")
+    coef_ddim, _, _ = d.engine_tables("ddim")
+    assert np.array_equal(coef, coef_ddim) and coef.shape == (50, 4)
+    import inspect
+    sig = inspect.signature(d.plms_sample_loop)
+    assert list(sig.parameters)[:3] == ["model", "shape", "noise"] and sig.parameters["order"].default == 2
+    assert "const_noise" in inspect.signature(d.p_sample_loop).parameters and "dump_steps" in inspect.signature(d.p_sample_loop).parameters
+    cfg = S.Config(a=1)
+    assert getattr(cfg, "missing", 7) == 7 and not hasattr(cfg, "missing") and cfg.a == 1
+    assert S.auto_max_batch(5, "cpu") == 5 and S.auto_max_batch(10 ** 6, "cpu") == 296
+    with pytest.raises(ValueError):
+        S.style_from_filename("/x/noseparator.wav")
