@@ -103,6 +103,60 @@ def zeggs():
     print("\n".join(report))
 
 
+def clips6():
+    """Six more 320-frame x 1000-step clips through the reference's own `sample.inference` (clip ids 1..6, style (id - 1) mod 6,
+    features / noise keyed by the clip id): widens the bf16 BVH parity test beyond the one Neutral clip of round 1."""
+    g = ZEGGS
+    torch.set_num_threads(os.cpu_count())
+    ref_sample, gd, SpacedDiffusion, space_timesteps = import_reference_zeggs()
+    sd = synthetic_state_dict(g, seed=0)
+    model = ref_model_zeggs(ref_sample, g, sd)
+    diff = make_ref_diffusion(gd, SpacedDiffusion, space_timesteps, None)
+    st = np.load(os.path.join(GOLD, "zeggs_mean_std.npz"))
+    A = types.SimpleNamespace(n_poses=88, audio_feat='wavlm')
+    out, report = {}, []
+    sn = StreamNoise()
+    for cid in range(1, 7):
+        style = [0] * 6
+        style[(cid - 1) % 6] = 1
+        feats = [synthetic_conditioning(g, 1, segment=sg, clip_offset=cid)["audio"] for sg in range(4)]
+        calls = {"i": 0}
+
+        def fake_wav2wavlm(model_, wav, device=None):
+            f = feats[calls["i"]]
+            sn.reset([cid], calls["i"])
+            calls["i"] += 1
+            return f
+        ref_sample.wav2wavlm = fake_wav2wavlm
+        ref_sample.mydevice = torch.device("cpu")
+        ref_sample.batch_size = 1
+        ref_sample.save_dir = tempfile.mkdtemp()
+        cap = {}
+        real = ref_sample.pose2bvh
+
+        def spy(poses, path, length, smoothing=False):
+            cap["poses"], cap["length"] = np.array(poses), length
+        ref_sample.pose2bvh = spy
+        import time
+        t0 = time.time()
+        with sn, torch.no_grad():
+            ref_sample.inference(A, None, np.zeros(320 * 800, dtype=np.float32), diff.p_sample_loop, model, n_frames=320,
+                                 smoothing=True, SG_filter=True, minibatch=True, skip_timesteps=0, style=style, seed=SEED)
+        ref_sample.pose2bvh = real
+        pos, eul = O.pose2bvh_values(cap["poses"], cap["length"], smoothing=True)       # tail pinned bit-exact in GOLDEN_REPORT.txt
+        norm = (cap["poses"] - np.array(st["mean"]).squeeze()) / np.clip(np.array(st["std"]).squeeze(), 0.01, None)
+        out[f"c{cid}/style"] = np.array(style)
+        out[f"c{cid}/norm_sub"] = norm[:, ::4].astype(np.float16)
+        out[f"c{cid}/positions"] = pos[::3].astype(np.float32)
+        out[f"c{cid}/rotations"] = eul[::3].astype(np.float32)
+        report.append(f"clip {cid} style {style}: reference inference {time.time() - t0:.1f} s, |norm|max {np.abs(norm).max():.3g}")
+        print(report[-1], flush=True)
+    np.savez_compressed(os.path.join(GOLD, "r2_clips6.npz"), **out)
+    with open(os.path.join(GOLD, "GOLDEN_REPORT_R2_CLIPS6.txt"), "w") as fh:
+        fh.write("Generated by oracle/gen_golden_r2.py clips6 against /root/reference/main (sample.inference, 4 segments x 1000 steps)\n"
+                 + "\n".join(report) + "\n")
+
+
 def beat():
     refb = os.path.join(REF, "BEAT-TWH-main")
     torch.set_num_threads(os.cpu_count())
@@ -238,4 +292,4 @@ def beat():
 
 
 if __name__ == "__main__":
-    {"zeggs": zeggs, "beat": beat}[sys.argv[1]]()
+    {"zeggs": zeggs, "beat": beat, "clips6": clips6}[sys.argv[1]]()
