@@ -279,3 +279,32 @@ def test_manifest_sharded_over_ranks_writes_identical_bvh(tmp_path):
     for a, b in zip(single, sharded):
         assert os.path.basename(a) == os.path.basename(b)
         assert open(a, "rb").read() == open(b, "rb").read(), os.path.basename(a)
+
+
+# ------------------------------------------------------------------------------------------------ bf16 BVH parity, widened
+@pytest.mark.slow
+def test_six_clips_six_styles_1000_steps_bf16_bvh_vs_reference_golden(gold_dir):
+    """BASELINE configs[1] over six more clips (ids 1..6, one per style) as ONE batch of the clip kernel: 320 frames = 4 segments
+    x 1000 DDPM steps, bf16 — final BVH joint values against the reference's own `sample.inference` per clip.
+    Same stated bound as the single-clip test of round 1: positions < 0.4 cm, Euler angles < 1.0 degree."""
+    from diffusestylegesture_b200 import sample as S
+    from diffusestylegesture_b200 import process_zeggs_bvh as PBZ
+    gold = np.load(os.path.join(gold_dir, "r2_clips6.npz"))
+    st = np.load(os.path.join(gold_dir, "zeggs_mean_std.npz"))
+    ids = list(range(1, 7))
+    m = _zeggs_model("bf16", max_batch=6)
+    d = create_gaussian_diffusion()
+    feats = [torch.cat([synthetic_conditioning(G, 1, segment=s, clip_offset=c)["audio"] for c in ids]) for s in range(4)]
+    styles = torch.tensor(np.stack([gold[f"c{c}/style"] for c in ids]), dtype=torch.float32)
+    assert sorted(int(i) for i in styles.argmax(1)) == list(range(6))
+    seq = S.inference_batch(m, d, feats, styles, seed=SEED, clip_ids=ids)
+    worst = (0.0, 0.0, 0.0)
+    for k, c in enumerate(ids):
+        err_n = np.abs(seq[k].numpy()[:, ::4] - gold[f"c{c}/norm_sub"].astype(np.float32)).max()
+        poses = O.denormalise(seq[k].numpy(), st["mean"], st["std"])
+        pos, eul = PBZ.pose2bvh_arrays(poses, 312, smoothing=True)
+        d_pos = np.abs(pos[::3] - gold[f"c{c}/positions"]).max()
+        d_eul = np.abs((eul[::3] - gold[f"c{c}/rotations"] + 180.0) % 360.0 - 180.0).max()
+        print(f"clip {c} (style {int(styles[k].argmax())}): normalised max err {err_n:.3g}; BVH positions {d_pos:.3g} cm, Euler {d_eul:.3g} deg")
+        worst = (max(worst[0], err_n), max(worst[1], d_pos), max(worst[2], d_eul))
+    assert worst[1] < 0.4 and worst[2] < 1.0, worst
