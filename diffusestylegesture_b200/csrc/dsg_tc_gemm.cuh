@@ -52,23 +52,18 @@ DSG_DEVINL void mbar_init(uint64_t* bar, uint32_t count) {
 DSG_DEVINL void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-// try_wait suspends the thread in hardware until the phase completes or a time limit passes; with the default (short) limit a
-// waiting warp wakes up and re-issues the poll every few hundred cycles — in the clip kernel 20 % of all executed warp
-// instructions were such polls, competing for issue slots with the working warps of the same scheduler.  The suspend-time
-// hint (ns) lets the hardware keep it parked; completion still wakes it immediately.
-#ifndef DSG_MBAR_SUSPEND_NS
-#define DSG_MBAR_SUSPEND_NS 20000
-#endif
+// (Measured in round 2: giving try_wait a suspend-time hint of 20 us does not reduce the step time — 307.6 vs 301.7 us — although
+// 20 % of the clip kernel's executed warp instructions are these polls; the plain form stays.)
 DSG_DEVINL void mbar_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
       "WAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
       "@p bra DONE_%=;\n\t"
       "bra WAIT_%=;\n\t"
       "DONE_%=:\n\t"
-      "}\n" ::"r"(smem_u32(bar)), "r"(parity), "r"((uint32_t)DSG_MBAR_SUSPEND_NS) : "memory");
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 DSG_DEVINL void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
