@@ -2,7 +2,12 @@
 variant BEAT-TWH-main/model/mdm.py:10-267).  It is a real ``torch.nn.Module`` whose ``state_dict`` keys and
 shapes are the reference's, so ``load_model_wo_clip(model, torch.load(ckpt))`` / ``model.to(dev).eval()``
 keep working — but it holds parameters only.  ``forward`` and the sampling loop execute in libdsg
-(hand-written sm_100a CUDA); there is no PyTorch compute path and no CPU fallback."""
+(hand-written sm_100a CUDA); there is no PyTorch compute path and no CPU fallback.
+
+``precision="bf16"`` (default) is NOT the reference's fp32 arithmetic: bf16 GEMM operands with fp32 accumulation, and in the
+persistent clip kernel a bf16 residual stream, fp16 ``linear2`` operands and the tanh form of GELU in packed fp16 instead of
+``F.gelu``'s erf form (mdm.py:79-86).  Stated tolerances: tests/test_gpu_tc.py, tests/test_gpu_r2.py; INTEGRATION.md.
+``precision="fp32"`` follows the reference's arithmetic to ~3e-6 (validation path)."""
 import torch
 from torch import nn
 
