@@ -311,24 +311,23 @@ def test_six_clips_six_styles_1000_steps_bf16_bvh_vs_reference_golden(gold_dir):
 
 
 # ------------------------------------------------------------------------------------------------ large-activation regime
-@pytest.mark.parametrize("gain", [2.0, 4.0])
+@pytest.mark.parametrize("gain", [4.0, 16.0])
 def test_bf16_denoiser_large_activation_regime(gain):
     """The bf16 engine deviates from the reference arithmetic (tanh-form GELU in packed fp16, fp16 linear2 operands, bf16 residual
     stream).  All golden vectors use default-init-scale weights, where FFN pre-activations are O(1).  Here every
     Linear weight is scaled by `gain` (pre-activations of |x| up to ~10-40, where erf- and tanh-GELU both saturate and fp16 must not
-    overflow): one denoiser call of the clip-kernel path against the fp32 oracle, error relative to the output scale."""
+    overflow): a 2-step loop of the clip kernel against the fp32 oracle, error relative to the output scale."""
     g = G
     sd = synthetic_state_dict(g, seed=0, gain=gain)
     y = synthetic_conditioning(g, 2, segment=0)
-    x = O.noise_tensor(SEED, [0, 1], 0, 0, (g.njoints, 1, g.n_poses))
-    t = torch.tensor([40, 900])
+    d = create_gaussian_diffusion([2])
     with torch.no_grad():
-        want = O.mdm_forward(sd, g, x, t, y)
+        want, _ = O.p_sample_loop(sd, g, O.Schedule(1000, [2]), y, 2, seed=SEED, segment=0)
     m = MDM(njoints=g.njoints, cond_mode='cross_local_attention3_style1', audio_feat='wavlm', n_seed=g.n_seed, precision="bf16", max_batch=2)
     load_model_wo_clip(m, sd)
     m.to('cuda:0').eval()
-    # the loop kernel is the production path: one DDIM step from x at index 0 of a 1-step schedule returns x0 = model(x, t0)
-    got = m(x, t, y=y).cpu()
+    # a 2-step loop runs the persistent clip kernel (the production path with the fp16 tanh GELU), not the multi-kernel denoiser
+    got = d.p_sample_loop(m, (2, g.njoints, 1, g.n_poses), clip_denoised=False, model_kwargs={'y': dict(y, noise_seed=SEED, segment=0)}).cpu()
     assert bool(torch.isfinite(got).all())
     scale = float(want.abs().max())
     mx, rms = _err(got, want)
