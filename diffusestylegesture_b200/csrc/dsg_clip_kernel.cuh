@@ -103,6 +103,9 @@ DSG_DEVINL void mbar_arrive(uint64_t* bar) {
 DSG_DEVINL void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 constexpr int NW = 12, NWT = NW * 32;          // worker warps / threads
 DSG_DEVINL void workers_sync() { asm volatile("bar.sync 1, 384;" ::: "memory"); }
+// the 4 worker warps that share a TMEM lane quarter (= one token row group): row statistics (LayerNorm sums, softmax max / sum)
+// are exchanged only among them, so they need not wait for the other two quarters
+DSG_DEVINL void quarter_sync(int q4) { asm volatile("bar.sync %0, 128;" ::"r"(2 + q4) : "memory"); }
 DSG_DEVINL void tmem_ld8_issue(uint32_t taddr, float* v) {
   uint32_t* r = reinterpret_cast<uint32_t*>(v);
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
@@ -605,7 +608,7 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
 #pragma unroll
       for (int i = 0; i < 64; ++i) { sum += v[i]; sq = fmaf(v[i], v[i], sq); }
       red_s[sub * 96 + r] = sum; red_q[sub * 96 + r] = sq;
-      workers_sync();
+      quarter_sync(q4);
       sum = red_s[r] + red_s[96 + r] + red_s[192 + r] + red_s[288 + r];
       sq = red_q[r] + red_q[96 + r] + red_q[192 + r] + red_q[288 + r];
       const float mean = sum * (1.0f / D);
@@ -856,7 +859,7 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
                 mx = fmaxf(mx, sc[i]);
               }
               red_s[sub * 96 + r] = mx;
-              workers_sync();
+              quarter_sync(q4);
               mx = fmaxf(fmaxf(red_s[r], red_s[96 + r]), fmaxf(red_s[192 + r], red_s[288 + r]));
               const float sl2 = 1.4426950408889634f * 0.125f;
               float sum = 0.f;

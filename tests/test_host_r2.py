@@ -145,3 +145,27 @@ def test_sampler_option_surface():
     assert S.auto_max_batch(5, "cpu") == 5 and S.auto_max_batch(10 ** 6, "cpu") == 296
     with pytest.raises(ValueError):
         S.style_from_filename("/x/noseparator.wav")
+
+
+def test_fp16_tanh_gelu_formula_saturates_and_is_accurate():
+    """The clip kernel's GELU (csrc/dsg_clip_kernel.cuh: gelu_h2) restated in torch.float16: 0.5 x (1 + tanh(x (c0 + c1 x^2))).
+    Against the reference's erf GELU (F.gelu, mdm.py:79-86): rms error on N(0, 1) pre-activations ~5e-4 (bf16 rounding of the exact
+    value: ~2e-3), exact saturation to x / 0 for large |x| — also where x^2 overflows fp16 (|x| > 255) — and no NaN up to the
+    fp16 range."""
+    import torch.nn.functional as F
+
+    def gelu_h(x):
+        x = x.to(torch.float16)
+        c1, c0 = torch.tensor(0.0356774081, dtype=torch.float16), torch.tensor(0.7978845608, dtype=torch.float16)
+        u = ((x * x) * c1 + c0) * x
+        hx = x * torch.tensor(0.5, dtype=torch.float16)
+        return (hx * torch.tanh(u.float()).to(torch.float16) + hx).float()
+    gen = torch.Generator().manual_seed(0)
+    x = torch.randn(200000, generator=gen)
+    e = gelu_h(x) - F.gelu(x)
+    e_bf16 = F.gelu(x).to(torch.bfloat16).float() - F.gelu(x)
+    assert float(e.pow(2).mean().sqrt()) < 1e-3 and float(e.pow(2).mean().sqrt()) < float(e_bf16.pow(2).mean().sqrt())
+    big = torch.tensor([-60000.0, -3000.0, -300.0, -40.0, -12.0, 12.0, 40.0, 300.0, 3000.0, 60000.0])
+    gb = gelu_h(big)
+    assert bool(torch.isfinite(gb).all())
+    assert torch.equal(gb[:5], torch.zeros(5)) and torch.allclose(gb[5:], big[5:].to(torch.float16).float())
