@@ -295,8 +295,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncwarp();
 
   // ===== epilogue (all 8 warps) =====
-  mbar_wait(tmem_full, 0);
-  tcgen05_fence_after();
+  if constexpr (EPI != EPI_LN && EPI != EPI_RESID && EPI != EPI_PCONV) {       // (those prefetch their residual chunk first)
+    mbar_wait(tmem_full, 0);
+    tcgen05_fence_after();
+  }
   const int wq = warp & 3, half = warp >> 2;
   const int rloc = wq * 32 + lane;
   const int row = ep.rows_per_z > 0 ? zb * ep.rows_per_z + m0 + rloc : m0 + rloc;
@@ -305,8 +307,30 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   float v[32];
 
   if constexpr (EPI == EPI_F32 || EPI == EPI_BF16 || EPI == EPI_GELU || EPI == EPI_RESID || EPI == EPI_PCONV) {
+    constexpr bool RMW = (EPI == EPI_RESID || EPI == EPI_PCONV);
+    float4 on[8];                                  // RMW epilogues: the output chunk of the next iteration, requested one ahead
+    const bool fast_rmw = RMW && (ep.ldc & 3) == 0;
+    if constexpr (RMW) {
+      if (fast_rmw && row_ok && n0 + half * 32 + 32 <= ep.N) {
+        const float* o0 = reinterpret_cast<const float*>(ep.out) + (long long)row * ep.ldc + n0 + half * 32;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) on[i] = *reinterpret_cast<const float4*>(o0 + 4 * i);
+      }
+      mbar_wait(tmem_full, 0);
+      tcgen05_fence_after();
+    }
 #pragma unroll 1
     for (int c = half * 32; c < BN; c += 64) {
+      float4 oc[8];
+      if constexpr (RMW) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) oc[i] = on[i];
+        if (fast_rmw && row_ok && c + 64 < BN && n0 + c + 64 + 32 <= ep.N) {
+          const float* o1 = reinterpret_cast<const float*>(ep.out) + (long long)row * ep.ldc + n0 + c + 64;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) on[i] = *reinterpret_cast<const float4*>(o1 + 4 * i);
+        }
+      }
       tmem_ld32(taddr + c, v);
       const int n = n0 + c;
       if (!row_ok || n >= ep.N) continue;
@@ -329,7 +353,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (n + 32 <= ep.N && (ep.ldc & 3) == 0) {
 #pragma unroll
           for (int i = 0; i < 32; i += 4) {
-            float4 t = *reinterpret_cast<float4*>(o + i);
+            float4 t = oc[i >> 2];
             t.x += v[i]; t.y += v[i + 1]; t.z += v[i + 2]; t.w += v[i + 3];
             *reinterpret_cast<float4*>(o + i) = t;
           }
@@ -383,13 +407,29 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // and writes the fp32 residual stream + its bf16 copy.
     float* xr = ep.xs + (long long)row * ep.N;
     float sum = 0.f, sq = 0.f;
+    // the residual chunk of the NEXT iteration is requested before this one is consumed (and the first one before the
+    // accumulator is waited for, see above): one L2 round trip per row-chunk would otherwise sit on the critical path
+    float4 rn[8];
+    if (row_ok) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) rn[i] = *reinterpret_cast<const float4*>(xr + half * 32 + 4 * i);
+    }
+    mbar_wait(tmem_full, 0);
+    tcgen05_fence_after();
 #pragma unroll 1
     for (int c = half * 32; c < BN; c += 64) {
+      float4 rc[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) rc[i] = rn[i];
+      if (row_ok && c + 64 < BN) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) rn[i] = *reinterpret_cast<const float4*>(xr + c + 64 + 4 * i);
+      }
       tmem_ld32(taddr + c, v);
       if (row_ok) {
 #pragma unroll
         for (int i = 0; i < 32; i += 4) {
-          const float4 r4 = *reinterpret_cast<const float4*>(xr + c + i);
+          const float4 r4 = rc[i >> 2];
           const float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + c + i));
           v[i] += r4.x + b4.x; v[i + 1] += r4.y + b4.y; v[i + 2] += r4.z + b4.z; v[i + 3] += r4.w + b4.w;
         }
