@@ -166,7 +166,8 @@ struct TcSmem {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
   static constexpr int RED_OFF = BAR_OFF + 128;                               // LayerNorm partials [2][128][2] fp32
-  static constexpr int TOTAL = RED_OFF + 2048 + 1024;                         // + alignment slack
+  static constexpr int PRM_OFF = RED_OFF + 2048;                              // this tile's bias | gamma | beta (3 x BN fp32)
+  static constexpr int TOTAL = PRM_OFF + 3 * BN * 4 + 1024;                   // + alignment slack
 };
 
 DSG_DEVINL float posterior_apply(int sampler, const float4 c, float x0, float xt, float z, bool nz) {
@@ -220,6 +221,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* tmem_full = empty_bar + STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
   float* red = reinterpret_cast<float*>(smem + SM::RED_OFF);     // [2 halves][128 rows][2] LayerNorm partials
+  // Per-column parameters of this tile are staged in shared memory once, under the barrier every CTA passes anyway: with the
+  // shared-memory carve-out at its maximum the L1 is a few KB, and a `__ldg(bias + c)` per 32-column chunk of the epilogue was
+  // one exposed L2 round trip per chunk and pass (ncu: the LayerNorm GEMM of the "+" path spent 25 of its 40 us there).
+  float* prm = reinterpret_cast<float*>(smem + SM::PRM_OFF);
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;     // warp-uniform for the compiler
   const int zdiv = ep.z_div > 0 ? ep.z_div : 1;
@@ -240,6 +245,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 2) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)TcTile<BN>::TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  {
+    for (int i = threadIdx.x; i < BN; i += blockDim.x) {
+      const int n = n0 + i;
+      prm[i] = (EPI != EPI_IN && ep.bias != nullptr && n < ep.N) ? __ldg(ep.bias + n) : 0.f;
+      if constexpr (EPI == EPI_LN) { prm[BN + i] = __ldg(ep.gamma + i); prm[2 * BN + i] = __ldg(ep.beta + i); }
+    }
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -337,12 +349,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (n + 32 <= ep.N) {
 #pragma unroll
         for (int i = 0; i < 32; i += 4) {
-          const float4 b4 = ep.bias ? __ldg(reinterpret_cast<const float4*>(ep.bias + n + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          const float4 b4 = *reinterpret_cast<const float4*>(prm + c + i);
           v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
         }
       } else {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) if (ep.bias && n + i < ep.N) v[i] += __ldg(ep.bias + n + i);
+        for (int i = 0; i < 32; ++i) if (n + i < ep.N) v[i] += prm[c + i];
       }
       if constexpr (EPI == EPI_GELU || EPI == EPI_PCONV) {
 #pragma unroll
@@ -430,7 +442,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
         for (int i = 0; i < 32; i += 4) {
           const float4 r4 = rc[i >> 2];
-          const float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + c + i));
+          const float4 b4 = *reinterpret_cast<const float4*>(prm + c + i);
           v[i] += r4.x + b4.x; v[i + 1] += r4.y + b4.y; v[i + 2] += r4.z + b4.z; v[i + 3] += r4.w + b4.w;
         }
 #pragma unroll
@@ -452,8 +464,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (!row_ok) continue;
 #pragma unroll
       for (int i = 0; i < 32; i += 4) {
-        const float4 g4 = __ldg(reinterpret_cast<const float4*>(ep.gamma + c + i));
-        const float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.beta + c + i));
+        const float4 g4 = *reinterpret_cast<const float4*>(prm + BN + c + i);
+        const float4 b4 = *reinterpret_cast<const float4*>(prm + 2 * BN + c + i);
         v[i] = (v[i] - mean) * rstd * g4.x + b4.x; v[i + 1] = (v[i + 1] - mean) * rstd * g4.y + b4.y;
         v[i + 2] = (v[i + 2] - mean) * rstd * g4.z + b4.z; v[i + 3] = (v[i + 3] - mean) * rstd * g4.w + b4.w;
       }
@@ -496,7 +508,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          const float x0 = v[i] + __ldg(ep.bias + min(n + i, ep.N - 1));
+          const float x0 = v[i] + prm[c + i];
           v[i] = (n + i < ep.N) ? posterior_apply(ep.sampler, cf, x0, xt[i], zz[i], nz) : 0.f;
         }
 #pragma unroll
@@ -505,7 +517,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       } else {
 #pragma unroll
         for (int i = 0; i < 32; ++i)
-          if (n + i < ep.N) reinterpret_cast<float*>(ep.out)[base + (long long)i * ep.T] = v[i] + __ldg(ep.bias + n + i);
+          if (n + i < ep.N) reinterpret_cast<float*>(ep.out)[base + (long long)i * ep.T] = v[i] + prm[c + i];
       }
     }
   }
