@@ -307,45 +307,30 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncwarp();
 
   // ===== epilogue (all 8 warps) =====
-  if constexpr (EPI != EPI_LN && EPI != EPI_RESID && EPI != EPI_PCONV) {       // (those prefetch their residual chunk first)
-    mbar_wait(tmem_full, 0);
-    tcgen05_fence_after();
-  }
+  mbar_wait(tmem_full, 0);
+  tcgen05_fence_after();
   const int wq = warp & 3, half = warp >> 2;
   const int rloc = wq * 32 + lane;
   const int row = ep.rows_per_z > 0 ? zb * ep.rows_per_z + m0 + rloc : m0 + rloc;
   const bool row_ok = ep.rows_per_z > 0 ? (m0 + rloc < ep.rows_per_z) : (row < ep.M);
   const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16);
   float v[32];
+  // coalesced epilogues: a 32 x 33 fp32 tile per warp in the (now idle) operand stages; rows of this warp: row_w0 .. +rows_w-1
+  float* tile = reinterpret_cast<float*>(smem) + warp * 1088;
+  const int row_w0 = row - lane;
+  const int rows_w = ep.rows_per_z > 0 ? min(32, max(0, ep.rows_per_z - (m0 + wq * 32))) : min(32, max(0, ep.M - (m0 + wq * 32)));
 
   if constexpr (EPI == EPI_F32 || EPI == EPI_BF16 || EPI == EPI_GELU || EPI == EPI_RESID || EPI == EPI_PCONV) {
     constexpr bool RMW = (EPI == EPI_RESID || EPI == EPI_PCONV);
-    float4 on[8];                                  // RMW epilogues: the output chunk of the next iteration, requested one ahead
-    const bool fast_rmw = RMW && (ep.ldc & 3) == 0;
-    if constexpr (RMW) {
-      if (fast_rmw && row_ok && n0 + half * 32 + 32 <= ep.N) {
-        const float* o0 = reinterpret_cast<const float*>(ep.out) + (long long)row * ep.ldc + n0 + half * 32;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) on[i] = *reinterpret_cast<const float4*>(o0 + 4 * i);
-      }
-      mbar_wait(tmem_full, 0);
-      tcgen05_fence_after();
-    }
 #pragma unroll 1
     for (int c = half * 32; c < BN; c += 64) {
-      float4 oc[8];
-      if constexpr (RMW) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) oc[i] = on[i];
-        if (fast_rmw && row_ok && c + 64 < BN && n0 + c + 64 + 32 <= ep.N) {
-          const float* o1 = reinterpret_cast<const float*>(ep.out) + (long long)row * ep.ldc + n0 + c + 64;
-#pragma unroll
-          for (int i = 0; i < 8; ++i) on[i] = *reinterpret_cast<const float4*>(o1 + 4 * i);
-        }
-      }
       tmem_ld32(taddr + c, v);
       const int n = n0 + c;
-      if (!row_ok || n >= ep.N) continue;
+      if constexpr (RMW) {
+        if (n >= ep.N) continue;                  // warp-uniform (the coalesced path below needs the whole warp)
+      } else {
+        if (!row_ok || n >= ep.N) continue;
+      }
       if (n + 32 <= ep.N) {
 #pragma unroll
         for (int i = 0; i < 32; i += 4) {
@@ -361,18 +346,17 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int i = 0; i < 32; ++i) v[i] = gelu_fast(v[i]);
       }
       if constexpr (EPI == EPI_RESID || EPI == EPI_PCONV) {
-        float* o = reinterpret_cast<float*>(ep.out) + (long long)row * ep.ldc + n;
-        if (n + 32 <= ep.N && (ep.ldc & 3) == 0) {
+        // out[row, n .. n+31] += v, coalesced: the warp's 32 x 32 block goes through its shared-memory tile and is applied row by
+        // row (lane = column: one 128-byte read-modify-write per row instead of 32 scattered 16-byte ones per instruction)
 #pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            float4 t = oc[i >> 2];
-            t.x += v[i]; t.y += v[i + 1]; t.z += v[i + 2]; t.w += v[i + 3];
-            *reinterpret_cast<float4*>(o + i) = t;
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) if (n + i < ep.N) o[i] += v[i];
-        }
+        for (int i = 0; i < 32; ++i) tile[lane * 33 + i] = v[i];
+        __syncwarp();
+        float* ob = reinterpret_cast<float*>(ep.out) + (long long)row_w0 * ep.ldc + n + lane;
+        const bool col_ok = n + lane < ep.N;
+#pragma unroll 8
+        for (int r = 0; r < 32; ++r)
+          if (col_ok && r < rows_w) ob[(long long)r * ep.ldc] += tile[r * 33 + lane];
+        __syncwarp();
       } else if constexpr (EPI == EPI_F32) {
         float* o = reinterpret_cast<float*>(ep.out) + (long long)row * ep.ldc + n;
         if (n + 32 <= ep.N && (ep.ldc & 3) == 0) {
@@ -417,38 +401,30 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // full rows live in this CTA (BN == N == D).  Pass 1 adds bias + residual, parks v back in TMEM and accumulates
     // this warp's share of the row statistics; the two column halves meet through shared memory; pass 2 normalises
     // and writes the fp32 residual stream + its bf16 copy.
-    float* xr = ep.xs + (long long)row * ep.N;
+    // Both passes touch global memory coalesced: the warp's 32 rows x 32 columns go through its shared-memory tile, and the
+    // residual read / the fp32 + bf16 writes are done row by row with lane = column (128- / 64-byte lines).  The row-per-thread
+    // form (32 scattered 16-byte accesses per instruction) made this epilogue 24 of the 41 us of the "+" LayerNorm GEMM.
     float sum = 0.f, sq = 0.f;
-    // the residual chunk of the NEXT iteration is requested before this one is consumed (and the first one before the
-    // accumulator is waited for, see above): one L2 round trip per row-chunk would otherwise sit on the critical path
-    float4 rn[8];
-    if (row_ok) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) rn[i] = *reinterpret_cast<const float4*>(xr + half * 32 + 4 * i);
-    }
-    mbar_wait(tmem_full, 0);
-    tcgen05_fence_after();
+    float* xw = ep.xs + (long long)row_w0 * ep.N;
 #pragma unroll 1
     for (int c = half * 32; c < BN; c += 64) {
-      float4 rc[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) rc[i] = rn[i];
-      if (row_ok && c + 64 < BN) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) rn[i] = *reinterpret_cast<const float4*>(xr + c + 64 + 4 * i);
-      }
       tmem_ld32(taddr + c, v);
-      if (row_ok) {
 #pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-          const float4 r4 = rc[i >> 2];
-          const float4 b4 = *reinterpret_cast<const float4*>(prm + c + i);
-          v[i] += r4.x + b4.x; v[i + 1] += r4.y + b4.y; v[i + 2] += r4.z + b4.z; v[i + 3] += r4.w + b4.w;
-        }
+      for (int i = 0; i < 32; ++i) tile[lane * 33 + i] = v[i];
+      __syncwarp();
+      const float bc = prm[c + lane];
+#pragma unroll 8
+      for (int r = 0; r < 32; ++r)
+        if (r < rows_w) tile[r * 33 + lane] += xw[(long long)r * ep.N + c + lane] + bc;
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = tile[lane * 33 + i];
+      if (row_ok) {
 #pragma unroll
         for (int i = 0; i < 32; ++i) { sum += v[i]; sq = fmaf(v[i], v[i], sq); }
       }
       tmem_st32(taddr + c, v);
+      __syncwarp();
     }
     red[(half * 128 + rloc) * 2] = sum;
     red[(half * 128 + rloc) * 2 + 1] = sq;
@@ -457,21 +433,31 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     sq = red[rloc * 2 + 1] + red[(128 + rloc) * 2 + 1];
     const float mean = sum / (float)BN;
     const float rstd = rsqrtf(fmaxf(sq / (float)BN - mean * mean, 0.f) + 1e-5f);
-    __nv_bfloat16* xbr = ep.xsb + (long long)row * ep.N;
+    __nv_bfloat16* xbw = ep.xsb + (long long)row_w0 * ep.N;
 #pragma unroll 1
     for (int c = half * 32; c < BN; c += 64) {
       tmem_ld32(taddr + c, v);
-      if (!row_ok) continue;
 #pragma unroll
       for (int i = 0; i < 32; i += 4) {
         const float4 g4 = *reinterpret_cast<const float4*>(prm + BN + c + i);
         const float4 b4 = *reinterpret_cast<const float4*>(prm + 2 * BN + c + i);
-        v[i] = (v[i] - mean) * rstd * g4.x + b4.x; v[i + 1] = (v[i + 1] - mean) * rstd * g4.y + b4.y;
-        v[i + 2] = (v[i + 2] - mean) * rstd * g4.z + b4.z; v[i + 3] = (v[i + 3] - mean) * rstd * g4.w + b4.w;
+        tile[lane * 33 + i] = (v[i] - mean) * rstd * g4.x + b4.x;
+        tile[lane * 33 + i + 1] = (v[i + 1] - mean) * rstd * g4.y + b4.y;
+        tile[lane * 33 + i + 2] = (v[i + 2] - mean) * rstd * g4.z + b4.z;
+        tile[lane * 33 + i + 3] = (v[i + 3] - mean) * rstd * g4.w + b4.w;
       }
-#pragma unroll
-      for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(xr + c + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-      store_bf16x32(xbr + c, v);
+      __syncwarp();
+#pragma unroll 8
+      for (int r = 0; r < 32; ++r)
+        if (r < rows_w) xw[(long long)r * ep.N + c + lane] = tile[r * 33 + lane];
+      const int cc = 2 * (lane & 15);
+#pragma unroll 8
+      for (int it = 0; it < 16; ++it) {
+        const int r = 2 * it + (lane >> 4);
+        if (r < rows_w)
+          *reinterpret_cast<__nv_bfloat162*>(xbw + (long long)r * ep.N + c + cc) = __floats2bfloat162_rn(tile[r * 33 + cc], tile[r * 33 + cc + 1]);
+      }
+      __syncwarp();
     }
   } else if constexpr (EPI == EPI_HEAD) {
     // row = b*S + s -> frame f = s-1 of clip b; column n = joint channel j.  For fixed j a warp's 32 rows are
