@@ -322,8 +322,28 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if constexpr (EPI == EPI_F32 || EPI == EPI_BF16 || EPI == EPI_GELU || EPI == EPI_RESID || EPI == EPI_PCONV) {
     constexpr bool RMW = (EPI == EPI_RESID || EPI == EPI_PCONV);
+    // read-modify-write epilogues: the old value is READ row-per-thread (8 independent 16-byte loads, next chunk one iteration
+    // ahead), the new one is WRITTEN coalesced through the warp's tile
+    float4 on[8];
+    const bool vec_ok = RMW && (ep.ldc & 3) == 0;
+    const float* orow = reinterpret_cast<const float*>(ep.out) + (long long)row * ep.ldc + n0;
+    if constexpr (RMW) {
+      if (vec_ok && row_ok && n0 + half * 32 + 32 <= ep.N) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) on[i] = *reinterpret_cast<const float4*>(orow + half * 32 + 4 * i);
+      }
+    }
 #pragma unroll 1
     for (int c = half * 32; c < BN; c += 64) {
+      float4 oc[8];
+      if constexpr (RMW) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) oc[i] = on[i];
+        if (vec_ok && row_ok && c + 64 < BN && n0 + c + 64 + 32 <= ep.N) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) on[i] = *reinterpret_cast<const float4*>(orow + c + 64 + 4 * i);
+        }
+      }
       tmem_ld32(taddr + c, v);
       const int n = n0 + c;
       if constexpr (RMW) {
@@ -348,15 +368,25 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if constexpr (EPI == EPI_RESID || EPI == EPI_PCONV) {
         // out[row, n .. n+31] += v, coalesced: the warp's 32 x 32 block goes through its shared-memory tile and is applied row by
         // row (lane = column: one 128-byte read-modify-write per row instead of 32 scattered 16-byte ones per instruction)
+        const bool full = vec_ok && n + 32 <= ep.N;                 // warp-uniform
+        if (full) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) tile[lane * 33 + i] = v[i];
-        __syncwarp();
-        float* ob = reinterpret_cast<float*>(ep.out) + (long long)row_w0 * ep.ldc + n + lane;
-        const bool col_ok = n + lane < ep.N;
+          for (int i = 0; i < 32; i += 4) {
+            const float4 t = oc[i >> 2];
+            tile[lane * 33 + i] = v[i] + t.x; tile[lane * 33 + i + 1] = v[i + 1] + t.y;
+            tile[lane * 33 + i + 2] = v[i + 2] + t.z; tile[lane * 33 + i + 3] = v[i + 3] + t.w;
+          }
+          __syncwarp();
+          float* ob = reinterpret_cast<float*>(ep.out) + (long long)row_w0 * ep.ldc + n + lane;
 #pragma unroll 8
-        for (int r = 0; r < 32; ++r)
-          if (col_ok && r < rows_w) ob[(long long)r * ep.ldc] += tile[r * 33 + lane];
-        __syncwarp();
+          for (int r = 0; r < 32; ++r)
+            if (r < rows_w) ob[(long long)r * ep.ldc] = tile[r * 33 + lane];
+          __syncwarp();
+        } else if (row_ok) {
+          float* o = reinterpret_cast<float*>(ep.out) + (long long)row * ep.ldc + n;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) if (n + i < ep.N) o[i] += v[i];
+        }
       } else if constexpr (EPI == EPI_F32) {
         float* o = reinterpret_cast<float*>(ep.out) + (long long)row * ep.ldc + n;
         if (n + 32 <= ep.N && (ep.ldc & 3) == 0) {
@@ -401,30 +431,40 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // full rows live in this CTA (BN == N == D).  Pass 1 adds bias + residual, parks v back in TMEM and accumulates
     // this warp's share of the row statistics; the two column halves meet through shared memory; pass 2 normalises
     // and writes the fp32 residual stream + its bf16 copy.
-    // Both passes touch global memory coalesced: the warp's 32 rows x 32 columns go through its shared-memory tile, and the
-    // residual read / the fp32 + bf16 writes are done row by row with lane = column (128- / 64-byte lines).  The row-per-thread
-    // form (32 scattered 16-byte accesses per instruction) made this epilogue 24 of the 41 us of the "+" LayerNorm GEMM.
+    // Pass 2 WRITES coalesced: the warp's 32 rows x 32 columns go through its shared-memory tile and leave row by row with
+    // lane = column (128- / 64-byte lines).  Row-per-thread stores are 32 scattered 16-byte transactions per instruction: the
+    // LSU, one transaction per clock, made pass 2 17 of the 41 us of the "+" LayerNorm GEMM (clock64 instrumentation).
     float sum = 0.f, sq = 0.f;
     float* xw = ep.xs + (long long)row_w0 * ep.N;
+    const float* xr = ep.xs + (long long)row * ep.N;
+    // pass 1 READS row-per-thread (8 independent 16-byte loads per chunk, the next chunk requested one iteration ahead: loads
+    // need memory-level parallelism, and a row-by-row coalesced loop serialises them — measured 41 -> 60 us)
+    float4 rn[8];
+    if (row_ok) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) rn[i] = *reinterpret_cast<const float4*>(xr + half * 32 + 4 * i);
+    }
 #pragma unroll 1
     for (int c = half * 32; c < BN; c += 64) {
+      float4 rc[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) rc[i] = rn[i];
+      if (row_ok && c + 64 < BN) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) rn[i] = *reinterpret_cast<const float4*>(xr + c + 64 + 4 * i);
+      }
       tmem_ld32(taddr + c, v);
-#pragma unroll
-      for (int i = 0; i < 32; ++i) tile[lane * 33 + i] = v[i];
-      __syncwarp();
-      const float bc = prm[c + lane];
-#pragma unroll 8
-      for (int r = 0; r < 32; ++r)
-        if (r < rows_w) tile[r * 33 + lane] += xw[(long long)r * ep.N + c + lane] + bc;
-      __syncwarp();
-#pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = tile[lane * 33 + i];
       if (row_ok) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          const float4 r4 = rc[i >> 2];
+          const float4 b4 = *reinterpret_cast<const float4*>(prm + c + i);
+          v[i] += r4.x + b4.x; v[i + 1] += r4.y + b4.y; v[i + 2] += r4.z + b4.z; v[i + 3] += r4.w + b4.w;
+        }
 #pragma unroll
         for (int i = 0; i < 32; ++i) { sum += v[i]; sq = fmaf(v[i], v[i], sq); }
       }
       tmem_st32(taddr + c, v);
-      __syncwarp();
     }
     red[(half * 128 + rloc) * 2] = sum;
     red[(half * 128 + rloc) * 2 + 1] = sq;
