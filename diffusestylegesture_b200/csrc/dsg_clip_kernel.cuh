@@ -135,6 +135,15 @@ DSG_DEVINL bool elect_one() { return elect_one_lane(); }
 DSG_DEVINL uint32_t uniform_u32(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
 // 2^x on MUFU.EX2 directly (ex2.approx.ftz: 2 ulp; exp2f() adds a subnormal-range rescale = 4 more instructions per element)
 DSG_DEVINL float ex2_fast(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+// packed fp32 pairs (sm_100: add / fma .f32x2 = FADD2 / FFMA2): two lanes per instruction for the LayerNorm statistics
+DSG_DEVINL void add2(float& a0, float& a1, float b0, float b1) {
+  asm("{\n\t.reg .b64 a, b;\n\tmov.b64 a, {%0, %1};\n\tmov.b64 b, {%2, %3};\n\tadd.rn.f32x2 a, a, b;\n\tmov.b64 {%0, %1}, a;\n\t}\n"
+      : "+f"(a0), "+f"(a1) : "f"(b0), "f"(b1));
+}
+DSG_DEVINL void fma2(float& c0, float& c1, float a0, float a1, float b0, float b1) {
+  asm("{\n\t.reg .b64 a, b, c;\n\tmov.b64 a, {%2, %3};\n\tmov.b64 b, {%4, %5};\n\tmov.b64 c, {%0, %1};\n\tfma.rn.f32x2 c, a, b, c;\n\t"
+      "mov.b64 {%0, %1}, c;\n\t}\n" : "+f"(c0), "+f"(c1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
 DSG_DEVINL void tie4(float* v) { asm volatile("" : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]) :: "memory"); }
 DSG_DEVINL void ldsm_x2(uint32_t& r0, uint32_t& r1, const void* p) {
   const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
@@ -602,23 +611,29 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
         unpack8(*reinterpret_cast<const uint4*>(XS + xs_off(r, col0 + i * 8)), rs);
         const float4 b0 = *reinterpret_cast<const float4*>(bias + col0 + i * 8);
         const float4 b1 = *reinterpret_cast<const float4*>(bias + col0 + i * 8 + 4);
-        v[i * 8 + 0] += rs[0] + b0.x; v[i * 8 + 1] += rs[1] + b0.y; v[i * 8 + 2] += rs[2] + b0.z; v[i * 8 + 3] += rs[3] + b0.w;
-        v[i * 8 + 4] += rs[4] + b1.x; v[i * 8 + 5] += rs[5] + b1.y; v[i * 8 + 6] += rs[6] + b1.z; v[i * 8 + 7] += rs[7] + b1.w;
+        add2(rs[0], rs[1], b0.x, b0.y); add2(rs[2], rs[3], b0.z, b0.w); add2(rs[4], rs[5], b1.x, b1.y); add2(rs[6], rs[7], b1.z, b1.w);
+        add2(v[i * 8 + 0], v[i * 8 + 1], rs[0], rs[1]); add2(v[i * 8 + 2], v[i * 8 + 3], rs[2], rs[3]);
+        add2(v[i * 8 + 4], v[i * 8 + 5], rs[4], rs[5]); add2(v[i * 8 + 6], v[i * 8 + 7], rs[6], rs[7]);
       }
+      float sum1 = 0.f, sq1 = 0.f;
 #pragma unroll
-      for (int i = 0; i < 64; ++i) { sum += v[i]; sq = fmaf(v[i], v[i], sq); }
+      for (int i = 0; i < 64; i += 2) { add2(sum, sum1, v[i], v[i + 1]); fma2(sq, sq1, v[i], v[i + 1], v[i], v[i + 1]); }
+      sum += sum1; sq += sq1;
       red_s[sub * 96 + r] = sum; red_q[sub * 96 + r] = sq;
       quarter_sync(q4);
       sum = red_s[r] + red_s[96 + r] + red_s[192 + r] + red_s[288 + r];
       sq = red_q[r] + red_q[96 + r] + red_q[192 + r] + red_q[288 + r];
       const float mean = sum * (1.0f / D);
       const float rstd = rsqrtf(fmaxf(sq * (1.0f / D) - mean * mean, 0.f) + 1e-5f);
+      const float nmr = -mean * rstd;                  // (v - mean) * rstd * g + b as two FMAs per element
 #pragma unroll
       for (int i = 0; i < 64; i += 4) {
         const float4 g4 = *reinterpret_cast<const float4*>(gamma + col0 + i);
         const float4 b4 = *reinterpret_cast<const float4*>(beta + col0 + i);
-        v[i] = (v[i] - mean) * rstd * g4.x + b4.x; v[i + 1] = (v[i + 1] - mean) * rstd * g4.y + b4.y;
-        v[i + 2] = (v[i + 2] - mean) * rstd * g4.z + b4.z; v[i + 3] = (v[i + 3] - mean) * rstd * g4.w + b4.w;
+        float t0 = nmr, t1 = nmr, t2 = nmr, t3 = nmr, o0 = b4.x, o1 = b4.y, o2 = b4.z, o3 = b4.w;
+        fma2(t0, t1, v[i], v[i + 1], rstd, rstd); fma2(t2, t3, v[i + 2], v[i + 3], rstd, rstd);
+        fma2(o0, o1, t0, t1, g4.x, g4.y); fma2(o2, o3, t2, t3, g4.z, g4.w);
+        v[i] = o0; v[i + 1] = o1; v[i + 2] = o2; v[i + 3] = o3;
       }
 #pragma unroll
       for (int i = 0; i < 8; ++i) *reinterpret_cast<uint4*>(XS + xs_off(r, col0 + i * 8)) = pack8(v + i * 8);
