@@ -140,6 +140,10 @@ DSG_DEVINL void add2(float& a0, float& a1, float b0, float b1) {
   asm("{\n\t.reg .b64 a, b;\n\tmov.b64 a, {%0, %1};\n\tmov.b64 b, {%2, %3};\n\tadd.rn.f32x2 a, a, b;\n\tmov.b64 {%0, %1}, a;\n\t}\n"
       : "+f"(a0), "+f"(a1) : "f"(b0), "f"(b1));
 }
+DSG_DEVINL void mul2(float& a0, float& a1, float b0, float b1) {
+  asm("{\n\t.reg .b64 a, b;\n\tmov.b64 a, {%0, %1};\n\tmov.b64 b, {%2, %3};\n\tmul.rn.f32x2 a, a, b;\n\tmov.b64 {%0, %1}, a;\n\t}\n"
+      : "+f"(a0), "+f"(a1) : "f"(b0), "f"(b1));
+}
 DSG_DEVINL void fma2(float& c0, float& c1, float a0, float a1, float b0, float b1) {
   asm("{\n\t.reg .b64 a, b, c;\n\tmov.b64 a, {%2, %3};\n\tmov.b64 b, {%4, %5};\n\tmov.b64 c, {%0, %1};\n\tfma.rn.f32x2 c, a, b, c;\n\t"
       "mov.b64 {%0, %1}, c;\n\t}\n" : "+f"(c0), "+f"(c1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
@@ -838,7 +842,7 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
 #pragma unroll
                 for (int i = 0; i < 16; i += 4) {
                   const float4 b4 = *reinterpret_cast<const float4*>(bq + i);
-                  v48[i] += b4.x; v48[i + 1] += b4.y; v48[i + 2] += b4.z; v48[i + 3] += b4.w;
+                  add2(v48[i], v48[i + 1], b4.x, b4.y); add2(v48[i + 2], v48[i + 3], b4.z, b4.w);
                 }
                 *reinterpret_cast<uint4*>(qd) = pack8(v48);          *reinterpret_cast<uint4*>(qd + LBO_Q) = pack8(v48 + 8);
                 *reinterpret_cast<uint4*>(kd) = pack8(v48 + 16);     *reinterpret_cast<uint4*>(kd + LBO_K) = pack8(v48 + 24);
@@ -880,7 +884,15 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
               float sum = 0.f;
               const float mxs = mx * sl2;
 #pragma unroll
-              for (int i = 0; i < 24; ++i) { sc[i] = ex2_fast(fmaf(sc[i], sl2, -mxs)); sum += sc[i]; }
+              for (int i = 0; i < 24; i += 2) {
+                float t0 = -mxs, t1 = -mxs;
+                fma2(t0, t1, sc[i], sc[i + 1], sl2, sl2);
+                sc[i] = ex2_fast(t0); sc[i + 1] = ex2_fast(t1);
+              }
+              float sum1 = 0.f;
+#pragma unroll
+              for (int i = 0; i < 24; i += 2) add2(sum, sum1, sc[i], sc[i + 1]);
+              sum += sum1;
               red_q[sub * 96 + r] = sum;
               uint8_t* pd = smem + AT_P + (sub * 3) * LBO_P + (r >> 3) * 128 + (r & 7) * 16;
               *reinterpret_cast<uint4*>(pd) = pack8(sc);
@@ -903,7 +915,7 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
               for (int i = 0; i < 16; i += 4) tie4(o16 + i);
               const float inv = 1.0f / (red_q[r] + red_q[96 + r] + red_q[192 + r] + red_q[288 + r]);
 #pragma unroll
-              for (int i = 0; i < 16; ++i) o16[i] *= inv;
+              for (int i = 0; i < 16; i += 2) mul2(o16[i], o16[i + 1], inv, inv);
               *reinterpret_cast<uint4*>(BUF + a_off(r, h * HD + sub * 16)) = pack8(o16);
               *reinterpret_cast<uint4*>(BUF + a_off(r, h * HD + sub * 16 + 8)) = pack8(o16 + 8);
             }
