@@ -44,8 +44,11 @@ def main():
         f.write(f"# ncu --set full --clock-control none -k {a.kernel}: {a.note}; {a.clips} clips x {a.steps} DDPM steps\n")
         f.write("metric,unit,value\n")
         for k, (u, v) in vals.items():
-            if a.all or k in KEEP or k.startswith("sm__inst_executed_pipe_") or "tensor" in k:
-                if v not in ("", "n/a"):
+            short = k.split(".")[0]
+            variant_ok = (".max" not in k and ".min" not in k and ".sum.p" not in k and "pct_of_peak_sustained_elapsed" not in k) or k in KEEP
+            if a.all or k in KEEP or (variant_ok and (short.startswith("sm__inst_executed_pipe_") or "tensor" in short)):
+                zero = v.replace(",", "").replace(".", "").strip("0") == ""
+                if v not in ("", "n/a") and (k in KEEP or (not zero and ".peak_sustained" not in k and ".per_second" not in k)):
                     f.write(f"{k},{u},{v}\n")
 
     def num(k):
