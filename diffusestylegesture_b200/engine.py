@@ -211,7 +211,6 @@ class Engine:
         opts = _LoopOpts(LOOP_CONST_NOISE if const_noise else 0, int(plms_order), 0, None, None)
         iters = dump = None
         if dump_steps is not None:
-            n_run = None
             iters = np.ascontiguousarray(sorted(set(int(i) for i in dump_steps if int(i) >= 0)), dtype=np.int32)
             dump = torch.empty((len(iters),) + tuple(x.shape), dtype=torch.float32, device=x.device)
             opts.n_dump, opts.dump_iters, opts.dump_out = len(iters), iters.ctypes.data, dump.data_ptr()

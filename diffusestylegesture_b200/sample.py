@@ -18,7 +18,6 @@ Differences from the reference, all additive:
 import argparse
 import math
 import os
-import sys
 from datetime import datetime
 from pprint import pprint
 

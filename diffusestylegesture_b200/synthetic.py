@@ -13,7 +13,7 @@ import zlib
 import numpy as np
 import torch
 
-from .config import ModelGeometry, state_dict_spec, VARIANT_ZEGGS_ATTN3
+from .config import ModelGeometry, state_dict_spec
 
 
 def _gen(seed, name):
