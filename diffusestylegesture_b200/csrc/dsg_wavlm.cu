@@ -238,7 +238,7 @@ static int wavlm_run(dsg_wavlm* m, int B, const float* wav_d, int n_poses, float
     CUDA_TRY(cudaGetLastError());
     { TcEpiArgs a = z; a.M = M; a.N = 3 * E; a.K = E; a.bias = m->bqkv[l]; a.out = m->qkv; a.ldc = 3 * E;
       TRY((launch_tc<256, 4, EPI_BF16>(e, m->tm_h, m->tm_qkv[l], a, 3 * E / 256, st))); }
-    wl::flash_attn_bias_kernel<<<B * H, 448, m->smem_fa, st>>>(m->qkv, m->att, m->gate, m->posbias, Lf, E, H);
+    wl::flash_attn_bias_kernel<<<B * H * 2, 224, m->smem_fa, st>>>(m->qkv, m->att, m->gate, m->posbias, Lf, E, H);
     e->launches++;
     CUDA_TRY(cudaGetLastError());
     { TcEpiArgs a = z; a.M = M; a.N = E; a.K = E; a.bias = w[WL_O_B]; a.out = m->x; a.ldc = E;

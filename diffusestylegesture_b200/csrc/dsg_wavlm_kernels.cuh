@@ -115,18 +115,22 @@ static __global__ void __launch_bounds__(256) gate_kernel(const __nv_bfloat16* _
 // ---------------------------------------------------------------------------------------------------
 // Self-attention with the gated relative-position bias as an additive mask (F.multi_head_attention_forward with a float
 // attn_mask, modules_WavLM.py:540-563): softmax(q k^T / 8 + gate[b,h,i] * pos_bias[h,i,j]) v, head dim 64, S <= 224.
-// One CTA per (clip, head), warp w owns query rows 16w..; keys are consumed in blocks of 32 with an online softmax
-// (running max / sum, FlashAttention-2 register layout) so the score tile never exceeds 16 x 32 per warp.
+// Two CTAs per (clip, head) — query rows [0, 112) and [112, 224), 7 warps each (two CTAs fit one SM and hide each other's
+// latencies; K / V are staged by both from L2) —, warp w owns 16 query rows; keys are consumed in blocks of 32 with an online
+// softmax (running max / sum, FlashAttention-2 register layout) so the score tile never exceeds 16 x 32 per warp.  The bias
+// values of the NEXT key block are requested before the current block's MMAs (they are scattered 4-byte reads of the
+// [H, S, S] table: one exposed L2 / L1 round trip per block otherwise).
 // ---------------------------------------------------------------------------------------------------
 constexpr int FA_LD = 72;
-static __global__ void __launch_bounds__(448) flash_attn_bias_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out,
+static __global__ void __launch_bounds__(224, 2) flash_attn_bias_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out,
                                                              const float* __restrict__ gate, const float* __restrict__ pos_bias,
                                                              int S, int E, int H) {
   extern __shared__ __align__(16) uint8_t fa_smem[];
   __nv_bfloat16* Qs = reinterpret_cast<__nv_bfloat16*>(fa_smem);
   __nv_bfloat16* Ks = Qs + 224 * FA_LD;
   __nv_bfloat16* Vs = Ks + 224 * FA_LD;
-  const int clip = blockIdx.x / H, head = blockIdx.x - clip * H;
+  const int rhalf = blockIdx.x & 1, ch = blockIdx.x >> 1;
+  const int clip = ch / H, head = ch - clip * H;
   const __nv_bfloat16* base = qkv + (long long)clip * S * 3 * E + head * 64;
   for (int e = threadIdx.x; e < 224 * 3 * 8; e += blockDim.x) {
     const int c8 = e & 7, rest = e >> 3, mat = rest % 3, r = rest / 3;
@@ -137,7 +141,7 @@ static __global__ void __launch_bounds__(448) flash_attn_bias_kernel(const __nv_
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int r0 = warp * 16;
+  const int r0 = (rhalf * 7 + warp) * 16;
   if (r0 >= S) return;
   const int g = lane >> 2, t2 = (lane & 3) * 2;
   const int ri0 = min(r0 + g, S - 1), ri1 = min(r0 + g + 8, S - 1);
@@ -155,7 +159,23 @@ static __global__ void __launch_bounds__(448) flash_attn_bias_kernel(const __nv_
 #pragma unroll
   for (int dt = 0; dt < 8; ++dt) { oc[dt][0] = oc[dt][1] = oc[dt][2] = oc[dt][3] = 0.f; }
   const int nkb = (S + 31) / 32;
+  float pbn[16];                                   // gated bias of the next key block: [nt][e] for row ri0, then for row ri1
+  auto load_bias = [&](int kb) {
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int cc = min(kb * 32 + nt * 8 + t2 + e, S - 1);
+        pbn[nt * 2 + e] = __ldg(pb0 + cc);
+        pbn[8 + nt * 2 + e] = __ldg(pb1 + cc);
+      }
+  };
+  load_bias(0);
   for (int kb = 0; kb < nkb; ++kb) {
+    float pbc[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) pbc[i] = pbn[i];
+    if (kb + 1 < nkb) load_bias(kb + 1);
     float sc[4][4];
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt) { sc[nt][0] = sc[nt][1] = sc[nt][2] = sc[nt][3] = 0.f; }
@@ -175,9 +195,8 @@ static __global__ void __launch_bounds__(448) flash_attn_bias_kernel(const __nv_
       for (int e = 0; e < 2; ++e) {
         const int c = kb * 32 + nt * 8 + t2 + e;
         const bool ok = c < S;
-        const int cc = ok ? c : S - 1;
-        sc[nt][e] = ok ? (sc[nt][e] * 0.125f + g0 * __ldg(pb0 + cc)) * L2E : -3.0e38f;
-        sc[nt][2 + e] = ok ? (sc[nt][2 + e] * 0.125f + g1 * __ldg(pb1 + cc)) * L2E : -3.0e38f;
+        sc[nt][e] = ok ? (sc[nt][e] * 0.125f + g0 * pbc[nt * 2 + e]) * L2E : -3.0e38f;
+        sc[nt][2 + e] = ok ? (sc[nt][2 + e] * 0.125f + g1 * pbc[8 + nt * 2 + e]) * L2E : -3.0e38f;
         bm0 = fmaxf(bm0, sc[nt][e]); bm1 = fmaxf(bm1, sc[nt][2 + e]);
       }
     bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 1)); bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 2));
