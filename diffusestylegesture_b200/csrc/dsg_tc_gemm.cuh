@@ -65,6 +65,9 @@ DSG_DEVINL void mbar_wait(uint64_t* bar, uint32_t parity) {
       "DONE_%=:\n\t"
       "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+DSG_DEVINL void mbar_arrive_cta(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 DSG_DEVINL void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");

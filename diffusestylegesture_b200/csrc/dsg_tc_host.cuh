@@ -7,6 +7,7 @@
 #include "dsg_engine.h"
 #include "dsg_tc_gemm.cuh"
 #include "dsg_tc_kernels.cuh"
+#include "dsg_tc_gemm_persistent.cuh"
 
 using bf16 = __nv_bfloat16;
 using namespace tc;
@@ -71,6 +72,43 @@ static int launch_tc(dsg_engine* e, const CUtensorMap& a, const CUtensorMap& b, 
   }
   dim3 grid(((ep.rows_per_z > 0 ? ep.rows_per_z : ep.M) + BM - 1) / BM, n_tiles, gz);
   tc_gemm_kernel<BN, STAGES, EPI><<<grid, 256, smem, st>>>(a, b, ep);
+  e->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return DSG_OK;
+}
+
+// fp32 row-major [rows, cols] output -> 2-D tensor map with a 32 x 32 box and 128-byte swizzle (the persistent GEMM's
+// cp.reduce.async.bulk.tensor epilogue: one reduce-add per warp block; rows / columns beyond the tensor are clipped)
+static int make_tmap_f32_out(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld) {
+  TRY(get_encode());
+  if (ld % 4) return dsg_fail(DSG_ERR_BAD_SHAPE, "tensor map: fp32 leading dimension %llu not a multiple of 4", (unsigned long long)ld);
+  const cuuint64_t gdim[2] = {cols, rows};
+  const cuuint64_t gstride[1] = {ld * sizeof(float)};
+  const cuuint32_t box[2] = {32, 32};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return dsg_fail(DSG_ERR_CUDA, "cuTensorMapEncodeTiled (fp32 out) failed (%d)", (int)r);
+  return DSG_OK;
+}
+
+// Persistent GEMM (dsg_tc_gemm_persistent.cuh): flat 2-D problems with N a multiple of 256-column tiles; `out_map` is the fp32
+// output map of EPI_RESID (ignored otherwise).  The weight map must have 256-row boxes.
+template <int EPI>
+static int launch_tc_persistent(dsg_engine* e, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap* out_map,
+                                const TcEpiArgs& ep, cudaStream_t st) {
+  constexpr int STAGES = (EPI == EPI_RESID) ? 3 : 4;
+  using SM = TcPersistSmem<STAGES, EPI>;
+  static bool configured = false;
+  if (!configured) {
+    CUDA_TRY(cudaFuncSetAttribute(tc_gemm_persistent_kernel<STAGES, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
+    configured = true;
+  }
+  const int m_tiles = (ep.M + BM - 1) / BM, n_tiles = (ep.N + 255) / 256;
+  const int sms = e->num_sms > 0 ? e->num_sms : 148;
+  const int grid = m_tiles * n_tiles < sms ? m_tiles * n_tiles : sms;
+  tc_gemm_persistent_kernel<STAGES, EPI><<<grid, 320, SM::TOTAL, st>>>(a, b, out_map ? *out_map : a, ep, m_tiles, n_tiles);
   e->launches++;
   CUDA_TRY(cudaGetLastError());
   return DSG_OK;

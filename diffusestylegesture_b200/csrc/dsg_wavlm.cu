@@ -34,9 +34,10 @@ struct dsg_wavlm {
   float *pcscale = nullptr, *posbias = nullptr;
   bf16 *act[2] = {nullptr, nullptr}, *hbf = nullptr, *qkv = nullptr, *att = nullptr, *ffb = nullptr, *xg = nullptr;
   float *convf = nullptr, *x = nullptr, *gate = nullptr, *lnout = nullptr, *wav = nullptr, *outbuf = nullptr;
-  CUtensorMap tm_conv_a[NCONV], tm_conv_w[NCONV], tm_feat, tm_proj, tm_xg, tm_pc, tm_h, tm_att, tm_ff;
+  CUtensorMap tm_conv_a[NCONV], tm_conv_w[NCONV], tm_feat, tm_proj, tm_xg, tm_pc, tm_h, tm_att, tm_ff, tm_xout;
   std::vector<CUtensorMap> tm_qkv, tm_o, tm_fc1, tm_fc2;
   size_t smem_fa = 0;
+  int xout_rows = 0;                    // rows the fp32 output map of the residual GEMMs was encoded for (= B * frames)
 };
 
 template <typename T>
@@ -202,6 +203,10 @@ static int wavlm_run(dsg_wavlm* m, int B, const float* wav_d, int n_poses, float
   const int Lf = m->L[NCONV - 1], M = B * Lf;
   TcEpiArgs z;
   memset(&z, 0, sizeof z);
+  if (m->xout_rows != M) {               // out_proj / fc2 accumulate into x through TMA reduce-adds: clip at this batch's rows
+    TRY(make_tmap_f32_out(&m->tm_xout, m->x, (uint64_t)M, E, E));
+    m->xout_rows = M;
+  }
   // ---- conv feature extractor
   wl::conv0_ln_gelu_kernel<<<m->eng.num_sms * 8, 256, 0, st>>>(wav_d, m->act[0], m->w[WV_CONV0], m->w[WV_CONV0 + 1], m->w[WV_CONV0 + 2], B, m->N, m->L[0]);
   e->launches++;
@@ -237,17 +242,17 @@ static int wavlm_run(dsg_wavlm* m, int B, const float* wav_d, int n_poses, float
     e->launches++;
     CUDA_TRY(cudaGetLastError());
     { TcEpiArgs a = z; a.M = M; a.N = 3 * E; a.K = E; a.bias = m->bqkv[l]; a.out = m->qkv; a.ldc = 3 * E;
-      TRY((launch_tc<256, 4, EPI_BF16>(e, m->tm_h, m->tm_qkv[l], a, 3 * E / 256, st))); }
+      TRY((launch_tc_persistent<EPI_BF16>(e, m->tm_h, m->tm_qkv[l], nullptr, a, st))); }
     wl::flash_attn_bias_kernel<<<B * H * 2, 224, m->smem_fa, st>>>(m->qkv, m->att, m->gate, m->posbias, Lf, E, H);
     e->launches++;
     CUDA_TRY(cudaGetLastError());
     { TcEpiArgs a = z; a.M = M; a.N = E; a.K = E; a.bias = w[WL_O_B]; a.out = m->x; a.ldc = E;
-      TRY((launch_tc<256, 4, EPI_RESID>(e, m->tm_att, m->tm_o[l], a, E / 256, st))); }
+      TRY((launch_tc_persistent<EPI_RESID>(e, m->tm_att, m->tm_o[l], &m->tm_xout, a, st))); }
     TRY((launch_ln<float, bf16, E, false>(m, m->x, m->hbf, w[WL_LN2_W], w[WL_LN2_B], M, st)));
     { TcEpiArgs a = z; a.M = M; a.N = FF; a.K = E; a.bias = w[WL_FC1_B]; a.out = m->ffb; a.ldc = FF;
-      TRY((launch_tc<256, 4, EPI_GELU>(e, m->tm_h, m->tm_fc1[l], a, FF / 256, st))); }
+      TRY((launch_tc_persistent<EPI_GELU>(e, m->tm_h, m->tm_fc1[l], nullptr, a, st))); }
     { TcEpiArgs a = z; a.M = M; a.N = E; a.K = FF; a.bias = w[WL_FC2_B]; a.out = m->x; a.ldc = E;
-      TRY((launch_tc<256, 4, EPI_RESID>(e, m->tm_ff, m->tm_fc2[l], a, E / 256, st))); }
+      TRY((launch_tc_persistent<EPI_RESID>(e, m->tm_ff, m->tm_fc2[l], &m->tm_xout, a, st))); }
   }
   // ---- encoder.layer_norm (WavLM.py:567-568) and the interpolation to n_poses frames (sample.py:47)
   float* const* wl_end = &m->w[WV_LAYER0 + WL_PER_LAYER * NLAYER];
