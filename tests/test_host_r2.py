@@ -169,3 +169,17 @@ def test_fp16_tanh_gelu_formula_saturates_and_is_accurate():
     gb = gelu_h(big)
     assert bool(torch.isfinite(gb).all())
     assert torch.equal(gb[:5], torch.zeros(5)) and torch.allclose(gb[5:], big[5:].to(torch.float16).float())
+
+
+def test_batch_cli_default_runs_many_clips_per_launch():
+    """the shipped YAML pinned max_batch = 1, so `--batch` ran one clip per engine launch.  Default is now 0 = auto
+    (min(clips, 2 x SM count)); `--max_batch N` overrides; the batch plan then groups many clips per launch."""
+    cfg = S.parse_cli([])
+    assert cfg.max_batch == 0
+    assert S.parse_cli(["--max_batch", "7"]).max_batch == 7
+    mb = int(cfg.max_batch or 0) or S.auto_max_batch(500, "cpu")
+    assert mb == 296
+    plan = S.plan_batches([4] * 300 + [2] * 10, mb)
+    assert [len(p) for p in plan] == [296, 4, 10]
+    model_kwargs = S.create_model_and_diffusion(cfg)[0]
+    assert model_kwargs.max_batch == 1          # the single-clip CLI path still builds a one-clip engine
