@@ -349,7 +349,7 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
           ph.wait(bars, B_HGO);
           if (nz) ph.wait(bars, B_ZR);
           const float* xc = P.x + (long long)clip * J * T;
-          const float* zc = P.z + (long long)clip * J * T;
+          const float* zc = P.z + (long long)blockIdx.x * J * T;          // noise scratch is per CTA (see the noise warp)
           auto hload = [&](int c) {
             const int sl = c & 3, j0 = c * HCH;
             const uint32_t bytes = (uint32_t)((J - j0 < HCH ? J - j0 : HCH) * T * 4);
@@ -495,7 +495,9 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
     Phases ph{1ull << B_ZF};
     for (int clip = blockIdx.x; clip < P.B; clip += gridDim.x) {
       const uint32_t cid = (uint32_t)P.clip_ids[clip];
-      float* zc = P.z + (long long)clip * J * T;
+      // the noise scratch is indexed by CTA, not by clip: 148 x 401 KB = 59 MB whatever the batch, small enough to be pinned in
+      // L2 by the launch's access-policy window (dsg_tc.cu: clip_run), so the step noise never travels to HBM and back
+      float* zc = P.z + (long long)blockIdx.x * J * T;
       for (int k = 0; k < P.n_run; ++k) {
         const int index = first_index - k;
         if (index == 0 || P.sampler != 0) continue;

@@ -41,6 +41,8 @@ struct dsg_tc_state {
   uint8_t* xa = nullptr;
   long long* prof = nullptr;
   CUtensorMap tm_cin, tm_c128, tm_c64, tm_cw2;
+  bool l2_limit_set = false;
+  size_t l2_window_max = 0;
 };
 
 #include "dsg_tc_host.cuh"
@@ -116,9 +118,42 @@ static int clip_run(dsg_engine* e, int B, float* xd, int k0, int n_run, int firs
   const int grid = B < e->num_sms ? B : e->num_sms;
   clip::pack_xa_kernel<<<dim3(clip::JPAD / 64, B), 256, 0, st>>>(xd, t->xa);       // x_T as the first step's A k-blocks
   e->launches++;
+  // The per-CTA noise scratch (grid x 401 KB) is written by the noise warp and bulk-copied back ~100-300 us later, every step: an
+  // access-policy window keeps it resident in L2 (persisting hits), so it costs no HBM traffic.  DSG_L2_PERSIST=0 disables it.
+  static const bool l2_persist = !(getenv("DSG_L2_PERSIST") && !strcmp(getenv("DSG_L2_PERSIST"), "0"));
+  bool window_set = false;
+  if (l2_persist) {
+    const size_t zbytes = (size_t)grid * clip::J * clip::T * sizeof(float);
+    if (!t->l2_limit_set) {
+      cudaDeviceProp prop;
+      if (cudaGetDeviceProperties(&prop, e->d.device) == cudaSuccess && prop.persistingL2CacheMaxSize > 0) {
+        const size_t want = (size_t)e->num_sms * clip::J * clip::T * sizeof(float);
+        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want < (size_t)prop.persistingL2CacheMaxSize ? want : (size_t)prop.persistingL2CacheMaxSize);
+        t->l2_window_max = (size_t)prop.accessPolicyMaxWindowSize;
+      }
+      cudaGetLastError();
+      t->l2_limit_set = true;
+    }
+    if (t->l2_window_max > 0) {
+      cudaStreamAttrValue av;
+      memset(&av, 0, sizeof av);
+      av.accessPolicyWindow.base_ptr = t->z;
+      av.accessPolicyWindow.num_bytes = zbytes < t->l2_window_max ? zbytes : t->l2_window_max;
+      av.accessPolicyWindow.hitRatio = 1.0f;
+      av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+      av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+      window_set = cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av) == cudaSuccess;
+      cudaGetLastError();
+    }
+  }
   if (p.prof) clip::clip_kernel<true><<<grid, 512, clip::SMEM_BYTES, st>>>(t->tm_cin, t->tm_c128, t->tm_c64, t->tm_cw2, p);
   else clip::clip_kernel<false><<<grid, 512, clip::SMEM_BYTES, st>>>(t->tm_cin, t->tm_c128, t->tm_c64, t->tm_cw2, p);
   e->launches++;
+  if (window_set) {                        // the window applies to launches made while it is set: take it off the caller's stream again
+    cudaStreamAttrValue av;
+    memset(&av, 0, sizeof av);
+    cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av);
+  }
   CUDA_TRY(cudaGetLastError());
   return DSG_OK;
 }
