@@ -5,17 +5,23 @@
 // 4 x 64 global heads, 8 x 32 local heads, window 11, T 88, J 1141) is compiled in.
 //
 // Warp roles (512 threads, warp = 4 * sub + q4; q4 = TMEM lane quarter = scheduler):
-//   q4 == 3 (rows 96..127 carry no token): 3 = TMA producer (weights, x_t k-blocks, x_t / z chunks)   7 = tcgen05.mma issuer
-//                                          11 = noise pre-draw (Philox)   15 = attention issuer (S = Q K^T, O = P V)
+//   q4 == 3 (rows 96..127 carry no token): 3 = TMA producer of the main weight ring (+ x_t k-blocks, x_t / z chunks)
+//                                          7 = tcgen05.mma issuer of the weight GEMMs       11 = noise pre-draw (Philox)
+//                                          15 = attention issuer (S = Q K^T, O = P V) and TMA producer of the linear2 ring
+//       These roles run WARP-CONVERGED with warp-uniform operands; only the tcgen05 / TMA instruction itself is issued by an
+//       elected lane (elect_one): inside `if (lane == 0)` the compiler serialises every UTCHMMA / UTMALDG through a
+//       uniform-register waterfall loop (~110 cycles of issue per MMA).
 //   q4 <  3: 12 worker warps (4 per scheduler): all epilogues, softmax, local attention; sub = column quarter of an epilogue.
-// Tensor memory (512 columns) = 4 quarters of 128 fp32 columns (Q0..Q3), handed back and forth per op with
-// ready/free mbarriers.  Shared memory:
+// Tensor memory (512 columns) = 4 quarters of 128 fp32 columns (Q0..Q3), handed back and forth per op with ready/free
+// mbarriers.  FFN: linear1(c) accumulates in Q2 / Q3, the GELU epilogue writes the fp16 hidden back over the first 64 columns of
+// the same quarter, linear2(c) reads it from there as a TENSOR-MEMORY A operand and accumulates into Q0|Q1.  Shared memory:
 //   XS  [128 x 256] bf16, UMMA K-major SWIZZLE_128B, stored row-group-major (xs_off)  — the residual stream AND the A
 //                                        operand; rows 96..127 carry no token: that contiguous 16 KB is the 4th weight stage
-//   BUF [128 x 256] bf16, same format — A ring of the input GEMM / rope'd h for local attention /
-//                                        attention output (A of out_proj) / FFN hidden chunk (fp16, A of linear2)
-//   W   3 x 16 KB weight stages ([128 or 64 rows] x 64 k) + the one inside XS, TMA + mbarrier ring
-//   AT_Q/K/P/V: per-head operands of the tcgen05 attention (no-swizzle core-matrix layouts, 40 KB); LayerNorm partials; barriers.
+//   BUF [128 x 256] bf16, same format — A ring of the input GEMM / rope'd h for local attention / attention output (A of
+//                                        out_proj) / 3 stages of the linear2 weight ring (FFN) / x_t, z chunks of the pose head
+//   W   3 x 16 KB weight stages ([128 or 64 rows] x 64 k) + the one inside XS: the main TMA + mbarrier ring
+//   AT_Q/K/P/V: per-head operands of the tcgen05 attention (no-swizzle core-matrix layouts, 40 KB; during the FFN: 2 stages of
+//   the linear2 ring); LayerNorm partials; per-layer parameters; barriers.
 #pragma once
 #include "dsg_tc_gemm.cuh"
 #include "dsg_tc_kernels.cuh"
