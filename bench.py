@@ -371,6 +371,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--profile-steps", type=int, default=40)
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: every rank runs --batch clips (default); strong: --global-batch clips are sharded over the ranks")
+    ap.add_argument("--global-batch", type=int, default=512, help="total clips of a --scaling strong run")
     ap.add_argument("--workload", default="zeggs", choices=["zeggs", "beat+", "twh+"],
                     help="zeggs = the metric's configuration (default); beat+ / twh+ = BASELINE config 4 (900-frame long-form clips)")
     ap.add_argument("--no-sweep", action="store_true", help="skip the batch sweep / config 3 / strong-scaling side measurements")
@@ -420,13 +423,20 @@ def main():
             precision = "fp32"
     # bf16: one persistent CTA per clip -> a multiple of the SM count (148) keeps every SM busy for the whole segment
     B = args.batch or (296 if precision == "bf16" else 8)
+    clip0 = rank * B
+    if args.scaling == "strong":            # contiguous shards of the global batch (distributed.shard_bounds); the slowest rank is timed
+        from diffusestylegesture_b200.distributed import shard_bounds
+        clip0, hi = shard_bounds(args.global_batch, rank, world)
+        B = hi - clip0
+        if B <= 0:
+            raise SystemExit(f"--global-batch {args.global_batch} leaves rank {rank} without clips")
+    total_clips = args.global_batch if args.scaling == "strong" else world * B
     model = make_model(precision, B)
     eng = model.get_engine(B)
     resp = '' if args.ddpm_steps == 1000 else [args.ddpm_steps]
     diffusion = create_gaussian_diffusion(resp)
     nseg = args.segments
     n_frames = nseg * (g.n_poses - g.n_seed)
-    clip0 = rank * B
     clip_ids = list(range(clip0, clip0 + B))
     conds = [synthetic_conditioning(g, B, segment=s, clip_offset=clip0) for s in range(nseg)]
     styles = conds[0]["style"]
@@ -447,7 +457,7 @@ def main():
         return S.inference_batch(model, diffusion, feats, styles_pin if out_device == "cpu" else styles, seed=123456,
                                  clip_ids=clip_ids, out_device=out_device, out=out_pin if out_device == "cpu" else None)
 
-    out_all_pin = torch.empty(world * B, n_frames - g.n_seed, g.njoints, dtype=torch.float32).pin_memory() \
+    out_all_pin = torch.empty(total_clips, n_frames - g.n_seed, g.njoints, dtype=torch.float32).pin_memory() \
         if (world > 1 and rank == 0 and not args.no_e2e) else None
 
     def e2e_step(feats, _unused):
@@ -456,7 +466,7 @@ def main():
         if world == 1:
             return one_step(feats, "cpu")
         loc = S.inference_batch(model, diffusion, feats, styles_pin, seed=123456, clip_ids=clip_ids, out_device=dev)
-        allm = gather_motions(loc, world * B)
+        allm = gather_motions(loc, total_clips)
         if rank == 0:
             out_all_pin.copy_(allm, non_blocking=True)
             torch.cuda.current_stream(dev).synchronize()
@@ -493,7 +503,7 @@ def main():
     log("timed region done: %.1f ms/step" % (total_ms / args.steps))
     clk = clocks.stop() if rank == 0 else None
     ms_per_step = total_ms / args.steps
-    frames_all = world * B * n_frames
+    frames_all = total_clips * n_frames
     value = frames_all / (ms_per_step * 1e-3)
 
     e2e = None
@@ -505,8 +515,8 @@ def main():
                "d2h_bytes_per_step": int(out_h.numel() * 4) if rank == 0 else 0,
                "collective": None if world == 1 else f"one gather of [{B}, {n_frames - g.n_seed}, {g.njoints}] fp32 per rank to rank 0 "
                                                      f"(NCCL, {world} ranks), inside the timed region; the D2H of all "
-                                                     f"{world * B} motions is rank 0's"}
-        assert rank != 0 or out_h.shape[0] == world * B
+                                                     f"{total_clips} motions is rank 0's"}
+        assert rank != 0 or out_h.shape[0] == total_clips
 
     # ---- parity tie: clip 0 of the run just timed (global clip id 0, seed 123456, style 0, synthetic features) IS the clip of
     # tests/golden/inference_zeggs_1000.npz (the reference's own 4-segment x 1000-step run): its noise is keyed by clip id, so
@@ -680,12 +690,12 @@ def main():
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
                 "dtype": "bf16" if precision == "bf16" else "f32", "data": "synthetic",
                 "config": {"workload": f"ZEGGS {n_frames}-frame clips = {nseg} sequential segments x 88 frames, "
                                        f"{diffusion.num_timesteps}-step DDPM, {B} clips per GPU, WavLM-shaped synthetic features "
                                        "[B,88,1024] per segment, synthetic weights (9.0 M params)",
-                           "clips_per_gpu": B, "global_clips": world * B, "segments": nseg, "ddpm_steps": diffusion.num_timesteps,
+                           "clips_per_gpu": B, "global_clips": total_clips, "segments": nseg, "ddpm_steps": diffusion.num_timesteps,
                            "precision": precision, "parallelism": f"clip-dp{world}", "l2": "flushed between timed iterations (256 MB write)"},
                 "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "kernels": kernels, "wavlm": wavlm,
                 "cpu_baseline": cb, "clocks": clk, "parity": parity, "sweep": sweep, "config3": config3, "strong": strong}
