@@ -54,6 +54,7 @@ constexpr int OFF_LNP = OFF_BUF + 3 * KT + 12288; // rows 96..127 of BUF k-tile 
 // pose-head phase: x_t / z chunks of 32 joint channels ([32][88] fp32 = 11,264 B each) are bulk-copied into 4 slots carved out
 // of BUF and the (idle) attention staging area
 constexpr int HCH = 32, HBYTES = HCH * T * 4, NHS = 4, NCHUNK = JPAD / HCH;
+constexpr int XA_ROWS_BYTES = 96 * 128;          // the token-carrying rows of one k-block of the x_t image
 constexpr int XA_BYTES = (JPAD / 64) * KT;       // per clip: x_t as bf16 A-operand k-blocks [18][128 x 64], SWIZZLE_128B image
 constexpr int OFF_BAR = OFF_B1 + 4096 + 3072;
 constexpr int SMEM_BYTES = OFF_BAR + 512 + 1024;
@@ -333,8 +334,10 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
             const int sl = kb & 3;
             ph.wait(bars, B_AEMPTY + sl);
             if (elect_one()) {
-              mbar_expect_tx(&bars[B_AFULL + sl], KT);
-              bulk_load(smem + OFF_BUF + sl * KT, xa + (long long)kb * KT, KT, &bars[B_AFULL + sl]);
+              // rows 0..95 of the k-block only (12 KB): rows 96..127 carry no token; what the stage holds there only reaches
+              // accumulator rows nobody reads
+              mbar_expect_tx(&bars[B_AFULL + sl], XA_ROWS_BYTES);
+              bulk_load(smem + OFF_BUF + sl * KT, xa + (long long)kb * KT, XA_ROWS_BYTES, &bars[B_AFULL + sl]);
             }
             __syncwarp();
             for (int nh = 0; nh < 2; ++nh) load(&tm_in, nh * 128, kb * 64, WSTAGE);
