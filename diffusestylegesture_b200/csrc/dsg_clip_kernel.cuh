@@ -984,36 +984,45 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
           const float4 cf = P.coef[index];
           const int f = r - 1;
           const bool ok = r >= 1 && r <= T;
-          for (int c = 0; c < NCHUNK; ++c) {
-            const int t = c >> 2, sl = c & 3;
-            if (sl == 0) ph.wait(bars, B_ACCR + (t & 3));
-            ph.wait(bars, B_HFULL + sl);
-            lap(PF_W_HEAD_WAIT);
+          for (int t = 0; t < JPAD / 128; ++t) {
+            // the whole 128-channel tile leaves tensor memory at once: one load round trip per tile instead of four, and the
+            // accumulator quarter goes back to the MMA thread before the posterior work instead of after it
+            float v32[4][8];                             // this thread's 8 channels of each of the tile's four chunks
+            ph.wait(bars, B_ACCR + (t & 3));
             tcgen05_fence_after();
-            const int j0 = c * HCH + sub * 8;
-            float v8[8];
-            tmem_ld8_issue(tlane + (t & 3) * 128 + sl * 32 + sub * 8, v8);
-            tmem_ld_wait();
-            if (ok && j0 < J) {
-              const float* xs = reinterpret_cast<const float*>(smem + hslot_x(sl)) + sub * 8 * T + f;
-              const float* zs = reinterpret_cast<const float*>(smem + hslot_z(sl)) + sub * 8 * T + f;
-              const float* bo = b1s + j0;
-              float* xg = xc + (long long)j0 * T + f;
 #pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const bool in = j0 + i < J;
-                const float xt = in ? xs[i * T] : 0.f, zz = (nz && in) ? zs[i * T] : 0.f;
-                const float x0 = v8[i] + bo[i];
-                v8[i] = in ? posterior_apply(P.sampler, cf, x0, xt, zz, nz) : 0.f;
-                if (in) xg[(long long)i * T] = v8[i];
+            for (int q = 0; q < 4; ++q) tmem_ld8_issue(tlane + (t & 3) * 128 + q * 32 + sub * 8, v32[q]);
+            tmem_ld_wait();
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { tie4(v32[q]); tie4(v32[q] + 4); }
+            release_acc(t & 3, -1, false, -1);
+#pragma unroll
+            for (int sl = 0; sl < 4; ++sl) {
+              const int c = 4 * t + sl;
+              ph.wait(bars, B_HFULL + sl);
+              lap(PF_W_HEAD_WAIT);
+              const int j0 = c * HCH + sub * 8;
+              float* v8 = v32[sl];
+              if (ok && j0 < J) {
+                const float* xs = reinterpret_cast<const float*>(smem + hslot_x(sl)) + sub * 8 * T + f;
+                const float* zs = reinterpret_cast<const float*>(smem + hslot_z(sl)) + sub * 8 * T + f;
+                const float* bo = b1s + j0;
+                float* xg = xc + (long long)j0 * T + f;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  const bool in = j0 + i < J;
+                  const float xt = in ? xs[i * T] : 0.f, zz = (nz && in) ? zs[i * T] : 0.f;
+                  const float x0 = v8[i] + bo[i];
+                  v8[i] = in ? posterior_apply(P.sampler, cf, x0, xt, zz, nz) : 0.f;
+                  if (in) xg[(long long)i * T] = v8[i];
+                }
+                uint8_t* row = xac + (long long)(j0 >> 6) * KT + (r >> 3) * 1024 + (r & 7) * 128;
+                *reinterpret_cast<uint4*>(row + ((((j0 & 63) >> 3) ^ (r & 7)) << 4)) = pack8(v8);
               }
-              uint8_t* row = xac + (long long)(j0 >> 6) * KT + (r >> 3) * 1024 + (r & 7) * 128;
-              *reinterpret_cast<uint4*>(row + ((((j0 & 63) >> 3) ^ (r & 7)) << 4)) = pack8(v8);
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&bars[B_HEMPTY + sl]);
+              lap(PF_W_HEAD);
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bars[B_HEMPTY + sl]);
-            if (sl == 3) release_acc(t & 3, -1, false, -1);
-            lap(PF_W_HEAD);
           }
         }
         fence_async_all();                               // x and its k-block image are read back by bulk copies (async proxy)
