@@ -72,7 +72,7 @@ constexpr int R_LAYER = 2048, R_QKV = 0, R_WO = 768, R_W1 = 1024, R_HEAD = NL * 
 // barrier indices
 enum { B_WFULL = 0, B_WEMPTY = 4, B_AFULL = 8, B_AEMPTY = 12, B_ACCR = 16, B_ACCF = 20, B_XSR = 24, B_BUFR = 25, B_BUFF = 27,
        B_ZR = 29, B_ZF = 30, B_HFULL = 31, B_HEMPTY = 35, B_HGO = 39, B_XAR = 40, B_QKR = 41, B_SR = 42, B_PR = 43, B_OR = 44,
-       B_W2FULL = 45, B_W2EMPTY = 50, B_COUNT = 55 };
+       B_W2FULL = 45, B_W2EMPTY = 50, B_RX = 55, B_PFREE = 56, B_COUNT = 57 };
 // FFN (round 2): the GELU'd hidden chunk never touches shared memory.  The epilogue writes it (fp16 pairs) back over the first
 // 64 columns of its own linear1 accumulator quarter with tcgen05.st, and linear2 reads it from there as a TENSOR-MEMORY A
 // operand (tcgen05.mma [d], [a_tmem], b_desc): no st.shared / proxy fence in the epilogue, no A re-reads by the tensor core, and
@@ -113,6 +113,50 @@ DSG_DEVINL void workers_sync() { asm volatile("bar.sync 1, 384;" ::: "memory"); 
 // the 4 worker warps that share a TMEM lane quarter (= one token row group): row statistics (LayerNorm sums, softmax max / sum)
 // are exchanged only among them, so they need not wait for the other two quarters
 DSG_DEVINL void quarter_sync(int q4) { asm volatile("bar.sync %0, 128;" ::"r"(2 + q4) : "memory"); }
+// ---- CTA-pair mode (CL = 2, see the header of clip_kernel): distributed shared memory + remote mbarrier arrivals
+DSG_DEVINL uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+DSG_DEVINL uint32_t map_to_cta(uint32_t saddr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
+DSG_DEVINL void st_remote16(uint32_t raddr, const uint4 v) {
+  asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(raddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+DSG_DEVINL void st_remote16f(uint32_t raddr, const float* v) {
+  asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(raddr), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
+}
+DSG_DEVINL void mbar_arrive_remote(uint32_t rbar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(rbar) : "memory");
+}
+DSG_DEVINL void mbar_arrive_release_cluster(uint64_t* bar) {      // local arrival that also publishes to the peer's observers
+  asm volatile("mbarrier.arrive.release.cluster.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+DSG_DEVINL void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {      // acquire at cluster scope: the arrivals may be remote
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAITC_%=:\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONEC_%=;\n\t"
+      "bra WAITC_%=;\n\t"
+      "DONEC_%=:\n\t"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// Diagnostic (off): every lane that stored into the peer's shared memory fences at cluster scope before the warp's one arrival.
+// Not needed: __syncwarp orders the lanes' stores before lane 0's release.cluster arrival (cumulativity), and where the data is
+// read through the async proxy each lane has already run fence.proxy.async (a MEMBAR.ALL.GPU).  Measured: 2 us per exchange.
+#ifndef DSG_PAIR_FENCE
+#define DSG_PAIR_FENCE 0
+#endif
+DSG_DEVINL void pair_fence() {
+#if DSG_PAIR_FENCE
+  asm volatile("fence.acq_rel.cluster;" ::: "memory");
+#endif
+}
+DSG_DEVINL void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 DSG_DEVINL void tmem_ld8_issue(uint32_t taddr, float* v) {
   uint32_t* r = reinterpret_cast<uint32_t*>(v);
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
@@ -226,6 +270,7 @@ DSG_DEVINL void tie32(float* v) {
 struct Phases {            // one phase bit per barrier, toggled on every completed wait
   uint64_t bits;
   DSG_DEVINL void wait(uint64_t* bars, int id) { mbar_wait(&bars[id], (uint32_t)(bits >> id) & 1u); bits ^= 1ull << id; }
+  DSG_DEVINL void waitc(uint64_t* bars, int id) { mbar_wait_cluster(&bars[id], (uint32_t)(bits >> id) & 1u); bits ^= 1ull << id; }
 };
 DSG_DEVINL void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -252,7 +297,19 @@ static __global__ void __launch_bounds__(256) pack_xa_kernel(const float* __rest
 }
 
 // ---------------------------------------------------------------------------------------------------
-template <bool PROF>
+// CL = 1: one CTA per clip.  CL = 2 (batches smaller than half the SMs): a CLUSTER of two CTAs per clip.  Each CTA keeps the
+// whole residual stream (XS) but streams and multiplies only its share of the weights:
+//   in_proj + global attention: 2 of the 4 heads per CTA; the head outputs are written into BOTH CTAs' BUF (distributed shared
+//       memory stores + a remote arrival on the peer's B_BUFR), so each CTA runs the full out_proj + LayerNorm 1 on its own;
+//   FFN: 4 of the 8 hidden chunks per CTA = a K-split of linear2; the fp32 partial sums are exchanged by ROW OWNERSHIP (rank 0
+//       owns TMEM lane quarters 0 and 2, rank 1 quarter 1): a non-owner warp writes its 64 columns into the owner's receive
+//       buffer (BUF: the linear2 ring keeps to the attention staging area in this mode), the owner adds them, runs LayerNorm 2
+//       and writes the bf16 rows into both CTAs' XS (remote arrivals on B_XSR);
+//   pose head: tiles 0..4 / 5..8; x_t and its bf16 image meet in global memory (B_XAR counts both CTAs' worker warps).
+//   The input GEMM, the local attention, out_proj and LayerNorm 1 are computed by both CTAs (16 % of the weight bytes).
+// Write-after-read across the pair is covered by data dependencies except for BUF, for which the peer sends a token (B_PFREE)
+// when its reads are over: once per step after the local attention (Z staging), once per layer after out_proj.
+template <bool PROF, int CL>
 __global__ void __launch_bounds__(512, 1)
 clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152]   box 128 x 64
             const __grid_constant__ CUtensorMap tm_w128,   // K=256 slab          box 128 x 64
@@ -275,9 +332,14 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
     mbar_init(&bars[B_XSR], NW);
     for (int i = 0; i < 2; ++i) { mbar_init(&bars[B_BUFR + i], NW); mbar_init(&bars[B_BUFF + i], 1); }
     mbar_init(&bars[B_ZR], 1); mbar_init(&bars[B_ZF], NW);
-    mbar_init(&bars[B_HGO], 1); mbar_init(&bars[B_XAR], NW);
+    mbar_init(&bars[B_HGO], 1); if constexpr (CL == 1) mbar_init(&bars[B_XAR], NW);
     mbar_init(&bars[B_QKR], NW); mbar_init(&bars[B_SR], 1); mbar_init(&bars[B_PR], NW); mbar_init(&bars[B_OR], 1);
     for (int i = 0; i < NS2; ++i) { mbar_init(&bars[B_W2FULL + i], 1); mbar_init(&bars[B_W2EMPTY + i], 1); }
+    if constexpr (CL > 1) {
+      mbar_init(&bars[B_XAR], CL * NW);                               // (re-initialised: both CTAs' workers publish x_t)
+      mbar_init(&bars[B_RX], cluster_ctarank() == 0 ? 8 : 4);         // the peer's non-owner warps of my row quarters
+      mbar_init(&bars[B_PFREE], 1);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_in) : "memory");
@@ -295,8 +357,17 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
   fence_async_smem();
   tcgen05_fence_before();
   __syncthreads();
+  if constexpr (CL > 1) cluster_sync_all();                // the peer's barriers are initialised before anything arrives on them
   tcgen05_fence_after();
   const uint32_t tmem = uniform_u32(*tmem_slot);           // (warp-uniform for the compiler: see elect_one)
+  // CTA pair: rank, the peer's shared memory window, this CTA's share of the heads / hidden chunks / pose-head tiles
+  const int rank = CL > 1 ? (int)uniform_u32(cluster_ctarank()) : 0;
+  const uint32_t peer_smem = CL > 1 ? uniform_u32(map_to_cta(smem_u32(smem), (uint32_t)(rank ^ 1))) : 0u;
+  const uint32_t peer_bars = peer_smem + OFF_BAR;
+  constexpr int NHL = NH / CL, NCH = 8 / CL, NS2L = CL == 1 ? NS2 : 2;
+  const int h_base = rank * NHL, c_base = rank * NCH;
+  const int tile0 = CL == 1 ? 0 : (rank == 0 ? 0 : 5), tile1 = CL == 1 ? JPAD / 128 : (rank == 0 ? 5 : JPAD / 128);
+  const int cid0 = (int)blockIdx.x / CL, ncl = (int)gridDim.x / CL;      // clip slot of this CTA (pair), clips in flight
   const int draw0 = (int)uniform_u32((uint32_t)P.lp->k);   // loop iteration of this launch's first step (dump_steps cuts the loop)
   const int first_index = (int)uniform_u32((uint32_t)P.lp->first_index) - draw0;
   const uint32_t key0 = P.lp->key0, key1 = P.lp->key1, segment = P.lp->segment;
@@ -321,13 +392,16 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
         slot = (slot + 1 == NS) ? 0 : slot + 1;
       };
       bool first = true;
-      for (int clip = blockIdx.x; clip < P.B; clip += gridDim.x)
+      for (int clip = cid0; clip < P.B; clip += ncl)
         for (int k = 0; k < P.n_run; ++k) {
           const int index = first_index - k;
           const bool nz = (index != 0) && (P.sampler == 0);
           // x_t as bf16 A k-blocks: written by pack_xa_kernel before the launch, afterwards by the head epilogue of the previous
           // step (B_XAR: those stores are complete and fenced for the async proxy, and BUF is no longer read)
-          if (!first) ph.wait(bars, B_XAR);
+          if (!first) {
+            if constexpr (CL > 1) { ph.waitc(bars, B_XAR); fence_async_all(); }     // half of the image was written by the peer
+            else ph.wait(bars, B_XAR);
+          }
           first = false;
           const uint8_t* xa = P.xa + (long long)clip * XA_BYTES;
           for (int kb = 0; kb < JPAD / 64; ++kb) {
@@ -344,21 +418,21 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
           }
           for (int l = 0; l < NL; ++l) {
             const int rb = l * R_LAYER;
-            for (int h = 0; h < NH; ++h) {              // per head: q|k rows as one 128-row box, v as a 64-row box
+            for (int h = h_base; h < h_base + NHL; ++h) {   // per head: q|k rows as one 128-row box, v as a 64-row box
               for (int kb = 0; kb < 4; ++kb) load(&tm_w128, rb + R_QKV + h * 192, kb * 64, WSTAGE);
               for (int kb = 0; kb < 4; ++kb) load(&tm_w64, rb + R_QKV + h * 192 + 128, kb * 64, WSTAGE / 2);
             }
             for (int nh = 0; nh < 2; ++nh)
               for (int kb = 0; kb < 4; ++kb) load(&tm_w128, rb + R_WO + nh * 128, kb * 64, WSTAGE);
             auto ff1 = [&](int c) { for (int kb = 0; kb < 4; ++kb) load(&tm_w128, rb + R_W1 + c * 128, kb * 64, WSTAGE); };
-            for (int c = 0; c < 8; ++c) ff1(c);          // (the linear2 tiles travel through their own ring: see the attention issuer)
+            for (int c = c_base; c < c_base + NCH; ++c) ff1(c);   // (the linear2 tiles travel through their own ring: see the attention issuer)
           }
           // pose head: weights + the x_t / z chunks the posterior needs (BUF is free once the last linear2 has completed)
-          for (int kb = 0; kb < 4; ++kb) load(&tm_w128, R_HEAD, kb * 64, WSTAGE);
+          for (int kb = 0; kb < 4; ++kb) load(&tm_w128, R_HEAD + tile0 * 128, kb * 64, WSTAGE);
           ph.wait(bars, B_HGO);
           if (nz) ph.wait(bars, B_ZR);
           const float* xc = P.x + (long long)clip * J * T;
-          const float* zc = P.z + (long long)blockIdx.x * J * T;          // noise scratch is per CTA (see the noise warp)
+          const float* zc = P.z + (long long)cid0 * J * T;                // noise scratch is per clip slot (see the noise warp)
           auto hload = [&](int c) {
             const int sl = c & 3, j0 = c * HCH;
             const uint32_t bytes = (uint32_t)((J - j0 < HCH ? J - j0 : HCH) * T * 4);
@@ -370,8 +444,8 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
             }
             __syncwarp();
           };
-          for (int c = 0; c < NHS; ++c) hload(c);
-          for (int t = 1; t < JPAD / 128; ++t) {
+          for (int c = 4 * tile0; c < 4 * tile0 + NHS; ++c) hload(c);
+          for (int t = tile0 + 1; t < tile1; ++t) {
             for (int kb = 0; kb < 4; ++kb) load(&tm_w128, R_HEAD + t * 128, kb * 64, WSTAGE);
             for (int c = 4 * t; c < 4 * t + 4; ++c) hload(c);
           }
@@ -419,10 +493,30 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
           tcgen05_commit(&bars[B_W2EMPTY + slot2]);
         }
         __syncwarp();
-        slot2 = (slot2 + 1 == NS2) ? 0 : slot2 + 1;
+        slot2 = (slot2 + 1 == NS2L) ? 0 : slot2 + 1;
       };
       auto owait = [&](int id) { const long long c0 = prof ? clock64() : 0; ph.wait(bars, id); if (prof) t_o += clock64() - c0; };
-      for (int clip = blockIdx.x; clip < P.B; clip += gridDim.x)
+      // a barrier the peer's workers arrive on too (acquire at cluster scope; the writers ran fence.proxy.async before arriving)
+      // taps in CTA-pair mode: XS is complete (both CTAs' rows) exactly when this warp has acquired B_XSR
+      auto pair_dump = [&](int slot, int clip) {
+        if constexpr (CL > 1) {
+          if (!(P.debug & 1) || rank != 0) return;
+          float* o = P.dbg + (long long)slot * P.dbg_slot + (long long)clip * S * D;
+          for (int i = lane; i < S * (D / 8); i += 32) {
+            const int rr = i / (D / 8), c8 = i % (D / 8);
+            float t8[8];
+            unpack8(*reinterpret_cast<const uint4*>(smem + OFF_XS + xs_off(rr, c8 * 8)), t8);
+            for (int j = 0; j < 8; ++j) o[(long long)rr * D + c8 * 8 + j] = t8[j];
+          }
+          __syncwarp();
+        }
+      };
+      auto owait_pair = [&](int id) {
+        if constexpr (CL > 1) {
+          const long long c0 = prof ? clock64() : 0; ph.waitc(bars, id); if (prof) t_o += clock64() - c0;
+        } else owait(id);
+      };
+      for (int clip = cid0; clip < P.B; clip += ncl)
         for (int k = 0; k < P.n_run; ++k) {
           // ---- input GEMM: A k-blocks staged by the workers into the BUF ring, D = Q0|Q1
           owait(B_ACCF + 0); owait(B_ACCF + 1);
@@ -435,7 +529,8 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
           if (elect_one()) { tcgen05_commit(&bars[B_ACCR + 0]); tcgen05_commit(&bars[B_ACCR + 1]); }
           for (int l = 0; l < NL; ++l) {
             // ---- in_proj, one head at a time into alternating TMEM halves: q | k | v = 3 x 64 columns
-            owait(B_XSR);
+            owait_pair(B_XSR);
+            pair_dump(l, clip);
             tcgen05_fence_after();
             const long long qkv_t0 = prof ? clock64() : 0, qkv_w0 = t_w, qkv_o0 = t_o;
             auto qkv = [&](int h) {
@@ -448,10 +543,10 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
             };
             // (S = Q K^T and O = P V of every head are issued by the attention issuer, warp 15; a head's TMEM half comes back
             //  after its O epilogue, which is what in_proj(h + 2) waits for)
-            for (int h = 0; h < NH; ++h) qkv(h);
+            for (int h = 0; h < NHL; ++h) qkv(h);
             if (prof) { t_qkv += clock64() - qkv_t0; t_qkv_w += t_w - qkv_w0; t_qkv_o += t_o - qkv_o0; }
             // ---- out_proj: A = attention output in BUF, D = Q0|Q1
-            owait(B_BUFR + 0); owait(B_BUFR + 1);
+            owait_pair(B_BUFR + 0); owait_pair(B_BUFR + 1);
             owait(B_ACCF + 0); owait(B_ACCF + 1);
             tcgen05_fence_after();
             for (int nh = 0; nh < 2; ++nh)
@@ -470,23 +565,26 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
               if (elect_one()) { tcgen05_commit(&bars[B_ACCR + 2 + (c & 1)]); }
             };
             ff1(0, true); ff1(1, true);
-            for (int c = 0; c < 8; ++c) {
+            for (int c = 0; c < NCH; ++c) {
               owait(B_BUFR + (c & 1));                   // hidden chunk c is in tensor memory
               if (c == 0) { owait(B_ACCF + 0); owait(B_ACCF + 1); }
               tcgen05_fence_after();
               for (int nh = 0; nh < 2; ++nh)
                 for (int kb2 = 0; kb2 < 2; ++kb2)
                   tile2((uint32_t)((2 + (c & 1)) * 128 + kb2 * 32), nh * 128, idesc128h, c > 0 || kb2 > 0);
-              if (c + 2 < 8) ff1(c + 2, false);
+              if (c + 2 < NCH) ff1(c + 2, false);
             }
             if (elect_one()) { tcgen05_commit(&bars[B_ACCR + 0]); tcgen05_commit(&bars[B_ACCR + 1]); }
             if (prof) { t_ffn += clock64() - ffn_t0; t_ffn_w += t_w - ffn_w0; t_ffn_o += t_o - ffn_o0; }
-            if (l == NL - 1 && elect_one()) tcgen05_commit(&bars[B_HGO]);      // every read of BUF by the tensor core is complete
+            // every read of BUF by the tensor core is complete (CTA pair: BUF is the receive buffer of LayerNorm 2 until the
+            // workers are through with it; they give the go themselves)
+            if (CL == 1 && l == NL - 1 && elect_one()) tcgen05_commit(&bars[B_HGO]);
           }
           // ---- pose head: 9 tiles of 128 joint channels, D rotates over the 4 quarters
-          owait(B_XSR);
+          owait_pair(B_XSR);
+          pair_dump(NL, clip);
           tcgen05_fence_after();
-          for (int t = 0; t < JPAD / 128; ++t) {
+          for (int t = 0; t < tile1 - tile0; ++t) {
             owait(B_ACCF + (t & 3));
             tcgen05_fence_after();
             for (int kb = 0; kb < 4; ++kb) tile(xs_addr + kb * 1024, (t & 3) * 128, idesc128, kb > 0, 4096);
@@ -502,16 +600,18 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
   } else if (q4 == 3 && sub == 2) {
     // =================================================== noise pre-draw ===================================================
     Phases ph{1ull << B_ZF};
-    for (int clip = blockIdx.x; clip < P.B; clip += gridDim.x) {
+    for (int clip = cid0; clip < P.B; clip += ncl) {
       const uint32_t cid = (uint32_t)P.clip_ids[clip];
-      // the noise scratch is indexed by CTA, not by clip: 148 x 401 KB = 59 MB whatever the batch, small enough to be pinned in
+      // the noise scratch is indexed by clip slot (CTA or CTA pair), not by clip: 148 x 401 KB = 59 MB whatever the batch, small enough to be pinned in
       // L2 by the launch's access-policy window (dsg_tc.cu: clip_run), so the step noise never travels to HBM and back
-      float* zc = P.z + (long long)blockIdx.x * J * T;
+      float* zc = P.z + (long long)cid0 * J * T;
+      // (CTA pair: each CTA draws the channels of its own pose-head tiles)
+      const int q_lo = tile0 * 128 * T / 4, q_hi = (tile1 * 128 < J ? tile1 * 128 : J) * T / 4;
       for (int k = 0; k < P.n_run; ++k) {
         const int index = first_index - k;
         if (index == 0 || P.sampler != 0) continue;
         ph.wait(bars, B_ZF);
-        for (int q = lane; q < J * T / 4; q += 32)
+        for (int q = q_lo + lane; q < q_hi; q += 32)
           *reinterpret_cast<float4*>(zc + 4 * q) = philox_normal4((uint32_t)q, (uint32_t)(1 + draw0 + k), cid, segment, key0, key1);
         fence_async_all();                               // z is read back through the async proxy (bulk copies)
         __syncwarp();
@@ -524,14 +624,14 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
     // S = Q K^T into columns [0, 96) of the head's TMEM half (the q | k accumulators are already extracted), then O = P V
     // into columns [96, 160).  Operands: canonical no-swizzle core-matrix layouts (AT_*); V is the MN-major B operand.
     {                                               // warp-converged, elected issue (see elect_one)
-      Phases ph{((1ull << NS2) - 1) << B_W2EMPTY};
+      Phases ph{((1ull << NS2L) - 1) << B_W2EMPTY};
       const uint32_t smem_addr0 = smem_u32(smem);
       constexpr uint32_t idesc_s = make_idesc_bf16(128, 96), idesc_o = make_idesc_bf16(128, 64) | (1u << 16);
       int slot2 = 0;
-      for (int clip = blockIdx.x; clip < P.B; clip += gridDim.x)
+      for (int clip = cid0; clip < P.B; clip += ncl)
         for (int k = 0; k < P.n_run; ++k)
           for (int l = 0; l < NL; ++l) {
-            for (int h = 0; h < NH; ++h) {
+            for (int h = 0; h < NHL; ++h) {
               const uint32_t d0 = tmem + (uint32_t)((h & 1) * 256);
               ph.wait(bars, B_QKR);
               tcgen05_fence_after();
@@ -558,7 +658,7 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
             // the attention operands are dead until the next layer, and BUF once out_proj has read it: they are the ring of this
             // layer's linear2 weight tiles
             bool buf_free = false;
-            for (int c = 0; c < 8; ++c)
+            for (int c = c_base; c < c_base + NCH; ++c)
               for (int nh = 0; nh < 2; ++nh)
                 for (int kb2 = 0; kb2 < 2; ++kb2) {
                   if (slot2 >= 2 && !buf_free) { ph.wait(bars, B_BUFF + 0); ph.wait(bars, B_BUFF + 1); buf_free = true; }
@@ -568,7 +668,7 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
                     tma_load_2d(smem + w2stage_off(slot2), &tm_w2, &bars[B_W2FULL + slot2], c * 128 + kb2 * 64, l * 256 + nh * 128);
                   }
                   __syncwarp();
-                  slot2 = (slot2 + 1 == NS2) ? 0 : slot2 + 1;
+                  slot2 = (slot2 + 1 == NS2L) ? 0 : slot2 + 1;
                 }
             if (!buf_free) { ph.wait(bars, B_BUFF + 0); ph.wait(bars, B_BUFF + 1); }      // keep the phase bits in step
           }
@@ -608,9 +708,11 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
     };
     // residual + bias + LayerNorm on the accumulator in Q0|Q1, result -> XS (bf16).  Thread = (row, 64-column quarter): the
     // row's 64 values stay in registers across the one barrier that exchanges the partial sums.
-    auto layernorm_epilogue = [&](const float* bias, const float* gamma, const float* beta) {
+    auto layernorm_epilogue = [&](const float* bias, const float* gamma, const float* beta, bool buf_token) {
       ph.wait(bars, B_ACCR + 0); ph.wait(bars, B_ACCR + 1);
       lap(PF_W_LN_WAIT);
+      // CTA pair: out_proj has read BUF for the last time, the peer may send its linear2 partial sums into it
+      if (CL > 1 && buf_token && wt == 0) mbar_arrive_remote(peer_bars + B_PFREE * 8);
       tcgen05_fence_after();
       float v[64];
       const int col0 = sub * 64;
@@ -658,8 +760,96 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
       // `red` is rewritten by the next LayerNorm only after several more worker barriers
       lap(PF_W_LN);
     };
+    // CTA pair, LayerNorm 2: the accumulator holds this CTA's K-half of linear2.  Rows are owned by TMEM lane quarter (rank 0:
+    // quarters 0 and 2, rank 1: quarter 1): a non-owner warp ships its 64 columns to the owner's receive buffer (BUF, laid out
+    // [column quarter][16-byte chunk][row] so that a warp's store is one contiguous 512 B), the owner adds them to its own half
+    // and runs the LayerNorm; the bf16 rows go into both CTAs' XS.
+    constexpr int RXROWS = 57;
+    auto layernorm_pair = [&](const float* bias, const float* gamma, const float* beta) {
+      ph.wait(bars, B_ACCR + 0); ph.wait(bars, B_ACCR + 1);
+      lap(PF_W_LN_WAIT);
+      tcgen05_fence_after();
+      float v[64];
+      const int col0 = sub * 64;
+      tmem_ld32_issue(tlane + col0, v); tmem_ld32_issue(tlane + col0 + 32, v + 32);
+      tmem_ld_wait(); tie32(v); tie32(v + 32);
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) { mbar_arrive(&bars[B_ACCF + 0]); mbar_arrive(&bars[B_ACCF + 1]); }
+      ph.waitc(bars, B_PFREE);                          // the peer's out_proj is done with its BUF (kept in step by every worker)
+      const bool mine = (q4 == 1) == (rank == 1);
+      const int rr = (q4 == 2 ? 32 : 0) + lane;         // row inside the owner's receive buffer
+      // (the partial sums travel as bf16: distributed shared memory moves ~20 B per cycle, and an fp32 exchange of 89 x 256 values
+      //  would cost more than the half of linear2 it saves; the rounding, 2^-9 of half the FFN output, is below that of the bf16
+      //  residual stream it is added to)
+      const uint32_t rx_off = (uint32_t)(OFF_BUF + (sub * 8 * RXROWS + rr) * 16);
+      if (!mine) {
+        if (r < S) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) st_remote16(peer_smem + rx_off + i * (RXROWS * 16), pack8(v + 8 * i));
+        }
+        pair_fence();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_remote(peer_bars + B_RX * 8);
+        lap(PF_W_LN);
+        return;
+      }
+      float sum = 0.f, sq = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float rs[8];
+        unpack8(*reinterpret_cast<const uint4*>(XS + xs_off(r, col0 + i * 8)), rs);
+        const float4 b0 = *reinterpret_cast<const float4*>(bias + col0 + i * 8);
+        const float4 b1 = *reinterpret_cast<const float4*>(bias + col0 + i * 8 + 4);
+        add2(rs[0], rs[1], b0.x, b0.y); add2(rs[2], rs[3], b0.z, b0.w); add2(rs[4], rs[5], b1.x, b1.y); add2(rs[6], rs[7], b1.z, b1.w);
+        add2(v[i * 8 + 0], v[i * 8 + 1], rs[0], rs[1]); add2(v[i * 8 + 2], v[i * 8 + 3], rs[2], rs[3]);
+        add2(v[i * 8 + 4], v[i * 8 + 5], rs[4], rs[5]); add2(v[i * 8 + 6], v[i * 8 + 7], rs[6], rs[7]);
+      }
+      ph.waitc(bars, B_RX);                             // (residual and bias are in: the wait for the peer is the last thing)
+      if (r < S) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float p8[8];
+          unpack8(*reinterpret_cast<const uint4*>(smem + rx_off + i * (RXROWS * 16)), p8);
+          add2(v[8 * i], v[8 * i + 1], p8[0], p8[1]); add2(v[8 * i + 2], v[8 * i + 3], p8[2], p8[3]);
+          add2(v[8 * i + 4], v[8 * i + 5], p8[4], p8[5]); add2(v[8 * i + 6], v[8 * i + 7], p8[6], p8[7]);
+        }
+      }
+      float sum1 = 0.f, sq1 = 0.f;
+#pragma unroll
+      for (int i = 0; i < 64; i += 2) { add2(sum, sum1, v[i], v[i + 1]); fma2(sq, sq1, v[i], v[i + 1], v[i], v[i + 1]); }
+      sum += sum1; sq += sq1;
+      red_s[sub * 96 + r] = sum; red_q[sub * 96 + r] = sq;
+      quarter_sync(q4);
+      sum = red_s[r] + red_s[96 + r] + red_s[192 + r] + red_s[288 + r];
+      sq = red_q[r] + red_q[96 + r] + red_q[192 + r] + red_q[288 + r];
+      const float mean = sum * (1.0f / D);
+      const float rstd = rsqrtf(fmaxf(sq * (1.0f / D) - mean * mean, 0.f) + 1e-5f);
+      const float nmr = -mean * rstd;
+#pragma unroll
+      for (int i = 0; i < 64; i += 4) {
+        const float4 g4 = *reinterpret_cast<const float4*>(gamma + col0 + i);
+        const float4 b4 = *reinterpret_cast<const float4*>(beta + col0 + i);
+        float t0 = nmr, t1 = nmr, t2 = nmr, t3 = nmr, o0 = b4.x, o1 = b4.y, o2 = b4.z, o3 = b4.w;
+        fma2(t0, t1, v[i], v[i + 1], rstd, rstd); fma2(t2, t3, v[i + 2], v[i + 3], rstd, rstd);
+        fma2(o0, o1, t0, t1, g4.x, g4.y); fma2(o2, o3, t2, t3, g4.z, g4.w);
+        v[i] = o0; v[i + 1] = o1; v[i + 2] = o2; v[i + 3] = o3;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const uint32_t off = (uint32_t)OFF_XS + xs_off(r, col0 + i * 8);
+        const uint4 u = pack8(v + i * 8);
+        *reinterpret_cast<uint4*>(smem + off) = u;
+        st_remote16(peer_smem + off, u);
+      }
+      fence_async_all();
+      pair_fence();
+      __syncwarp();
+      if (lane == 0) { mbar_arrive(&bars[B_XSR]); mbar_arrive_remote(peer_bars + B_XSR * 8); }
+      lap(PF_W_LN);
+    };
     auto debug_dump = [&](int slot, int clip) {
-      if (!P.debug) return;
+      if (!(P.debug & 1) || CL > 1) return;                  // (CTA pair: the MMA warp writes the taps, see pair_dump)
       workers_sync();
       if (r < S) {
         float* o = P.dbg + (long long)slot * P.dbg_slot + ((long long)clip * S + r) * D + sub * 64;
@@ -671,7 +861,7 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
       }
     };
 
-    for (int clip = blockIdx.x; clip < P.B; clip += gridDim.x) {
+    for (int clip = cid0; clip < P.B; clip += ncl) {
       float* xc = P.x + (long long)clip * J * T;
       uint8_t* xac = P.xa + (long long)clip * XA_BYTES;
       const float* condc = P.cond + (long long)clip * T * D;
@@ -806,6 +996,7 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
         fence_async_smem();
         workers_sync();                                  // Z staging (BUF) is dead from here on
         if (lane == 0) mbar_arrive(&bars[B_XSR]);
+        if (CL > 1 && wt == 0) mbar_arrive_remote(peer_bars + B_PFREE * 8);      // ... and the peer may write head outputs into it
         lap(PF_W_LOCAL);
         debug_dump(0, clip);
 
@@ -832,8 +1023,8 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
             }
           }
           workers_sync();
-          for (int h = 0; h < NH; ++h) {
-            const int hb = h & 1;
+          for (int hl = 0; hl < NHL; ++hl) {
+            const int hb = hl & 1, h = h_base + hl;
             ph.wait(bars, B_ACCR + 2 * hb); ph.wait(bars, B_ACCR + 2 * hb + 1);
             lap(PF_W_QKV_WAIT);
             tcgen05_fence_after();
@@ -865,7 +1056,12 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
                 *reinterpret_cast<uint4*>(vd) = z4; *reinterpret_cast<uint4*>(vd + 128) = z4;
               }
             }
-            if (l > 0 && hb == 0) ph.wait(bars, B_BUFF + (h >> 1));    // linear2 of the previous layer has consumed this BUF half
+            if constexpr (CL == 1) {
+              if (l > 0 && hb == 0) ph.wait(bars, B_BUFF + (h >> 1));  // linear2 of the previous layer has consumed this BUF half
+            } else {
+              if (l > 0 && hb == 0) { ph.wait(bars, B_BUFF + 0); ph.wait(bars, B_BUFF + 1); }
+              if (l == 0 && hl == 0) ph.waitc(bars, B_PFREE);          // the peer's local attention is done with its Z staging
+            }
             tcgen05_fence_before();
             fence_async_smem();
             __syncwarp();
@@ -927,22 +1123,29 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
               const float inv = 1.0f / (red_q[r] + red_q[96 + r] + red_q[192 + r] + red_q[288 + r]);
 #pragma unroll
               for (int i = 0; i < 16; i += 2) mul2(o16[i], o16[i + 1], inv, inv);
-              *reinterpret_cast<uint4*>(BUF + a_off(r, h * HD + sub * 16)) = pack8(o16);
-              *reinterpret_cast<uint4*>(BUF + a_off(r, h * HD + sub * 16 + 8)) = pack8(o16 + 8);
+              const uint32_t o_off = (uint32_t)OFF_BUF + a_off(r, h * HD + sub * 16), o_off8 = (uint32_t)OFF_BUF + a_off(r, h * HD + sub * 16 + 8);
+              const uint4 u0 = pack8(o16), u1 = pack8(o16 + 8);
+              *reinterpret_cast<uint4*>(smem + o_off) = u0;
+              *reinterpret_cast<uint4*>(smem + o_off8) = u1;
+              if constexpr (CL > 1) { st_remote16(peer_smem + o_off, u0); st_remote16(peer_smem + o_off8, u1); }   // out_proj runs on both CTAs
             }
             tcgen05_fence_before();
-            fence_async_smem();
+            // (CTA pair: the tensor core reads BUF only after the second head, whose fence covers this thread's stores of both)
+            if constexpr (CL > 1) { if (hb == 1) { fence_async_all(); pair_fence(); } } else fence_async_smem();
             __syncwarp();
             if (lane == 0) {
               mbar_arrive(&bars[B_ACCF + 2 * hb]); mbar_arrive(&bars[B_ACCF + 2 * hb + 1]);      // the head's TMEM half is free
-              if (hb == 1) mbar_arrive(&bars[B_BUFR + (h >> 1)]);                                  // both heads of this BUF half are written
+              if (hb == 1) {                                                                       // both heads of this BUF half are written
+                mbar_arrive(&bars[B_BUFR + (h >> 1)]);
+                if constexpr (CL > 1) mbar_arrive_remote(peer_bars + (B_BUFR + (h >> 1)) * 8);
+              }
             }
             lap(PF_W_ATT_MERGE);
           }
-          layernorm_epilogue(b1s + 768, lnp, lnp + 256);
+          layernorm_epilogue(b1s + 768, lnp, lnp + 256, true);
           // ---- FFN: GELU epilogue per 128-unit chunk; the fp16 hidden goes back into the chunk's own accumulator quarter
           // (columns 0..63: column j = units (j, 64 + j)) as the tensor-memory A operand of linear2
-          for (int c = 0; c < 8; ++c) {
+          for (int c = 0; c < NCH; ++c) {
             const int qd = 2 + (c & 1);
             ph.wait(bars, B_ACCR + qd);
             lap(PF_W_GELU_WAIT);
@@ -955,7 +1158,7 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
               tmem_ld_wait(); tie32(va);
               // GELU in packed fp16 (tanh form on MUFU.TANH, 4 instructions per element): the hidden is stored as fp16, which
               // keeps 3 more mantissa bits than the bf16 it replaces; |half-tanh GELU - exact| rms 5e-4 vs 2e-3 for bf16(exact)
-              const __half* b1h = reinterpret_cast<const __half*>(b1s) + c * 128 + cc0;
+              const __half* b1h = reinterpret_cast<const __half*>(b1s) + (c_base + c) * 128 + cc0;
               uint32_t ha[16];
 #pragma unroll
               for (int i = 0; i < 16; ++i)
@@ -966,36 +1169,42 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
             __syncwarp();
             if (lane == 0) {
               mbar_arrive(&bars[B_BUFR + (c & 1)]);
-              if (c >= 6) mbar_arrive(&bars[B_ACCF + qd]);      // the quarter's next user (in_proj of the next layer / the pose head) waits for this
+              if (c >= NCH - 2) mbar_arrive(&bars[B_ACCF + qd]);      // the quarter's next user (in_proj of the next layer / the pose head) waits for this
             }
             lap(PF_W_GELU);
           }
-          layernorm_epilogue(b1s + 1024, lnp + 512, lnp + 768);
+          if constexpr (CL > 1) layernorm_pair(b1s + 1024, lnp + 512, lnp + 768);
+          else layernorm_epilogue(b1s + 1024, lnp + 512, lnp + 768, false);
           debug_dump(l + 1, clip);
         }
 
         // ---------------- pose head + posterior: x <- f(x0, x, z) in place (fp32, global) and as next step's bf16 A k-blocks.
         // Chunk c = 32 joint channels (TMEM quarter (c >> 2) & 3, columns (c & 3) * 32); the four column quarters take 8 each.
-        // the layer parameters are dead (every warp is past the barrier of the last LayerNorm): the head bias takes their place
+        // the head bias takes the place of the layer parameters once EVERY warp has read the linear2 bias of the last LayerNorm
+        // (CTA pair: the non-owner warps leave that LayerNorm long before the owners have their partial sums)
+        workers_sync();
         for (int i = wt; i < JPAD; i += NWT) b1s[i] = __ldg(P.bout + i);
         workers_sync();
+        // CTA pair: every worker is through with the LayerNorm 2 receive buffer (BUF): the x_t / z chunks may land there
+        if (CL > 1 && wt == 0) mbar_arrive(&bars[B_HGO]);
         lap(PF_W_ZWAIT);
         {
           const float4 cf = P.coef[index];
           const int f = r - 1;
           const bool ok = r >= 1 && r <= T;
-          for (int t = 0; t < JPAD / 128; ++t) {
+          for (int tt = 0; tt < tile1 - tile0; ++tt) {
+            const int t = tile0 + tt;
             // the whole 128-channel tile leaves tensor memory at once: one load round trip per tile instead of four, and the
             // accumulator quarter goes back to the MMA thread before the posterior work instead of after it
             float v32[4][8];                             // this thread's 8 channels of each of the tile's four chunks
-            ph.wait(bars, B_ACCR + (t & 3));
+            ph.wait(bars, B_ACCR + (tt & 3));
             tcgen05_fence_after();
 #pragma unroll
-            for (int q = 0; q < 4; ++q) tmem_ld8_issue(tlane + (t & 3) * 128 + q * 32 + sub * 8, v32[q]);
+            for (int q = 0; q < 4; ++q) tmem_ld8_issue(tlane + (tt & 3) * 128 + q * 32 + sub * 8, v32[q]);
             tmem_ld_wait();
 #pragma unroll
             for (int q = 0; q < 4; ++q) { tie4(v32[q]); tie4(v32[q] + 4); }
-            release_acc(t & 3, -1, false, -1);
+            release_acc(tt & 3, -1, false, -1);
 #pragma unroll
             for (int sl = 0; sl < 4; ++sl) {
               const int c = 4 * t + sl;
@@ -1026,14 +1235,20 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
           }
         }
         fence_async_all();                               // x and its k-block image are read back by bulk copies (async proxy)
+        if constexpr (CL > 1) pair_fence();
         __syncwarp();
-        if (lane == 0) { mbar_arrive(&bars[B_XAR]); if (nz) mbar_arrive(&bars[B_ZF]); }
+        if (lane == 0) {
+          if constexpr (CL > 1) { mbar_arrive_release_cluster(&bars[B_XAR]); mbar_arrive_remote(peer_bars + B_XAR * 8); }
+          else mbar_arrive(&bars[B_XAR]);
+          if (nz) mbar_arrive(&bars[B_ZF]);
+        }
       }
     }
     if constexpr (PROF) { if (prof) for (int i = PF_W_STAGE; i <= PF_W_ATT_MERGE; ++i) P.prof[i] = pf[i]; }
   }
   tcgen05_fence_before();
   __syncthreads();
+  if constexpr (CL > 1) cluster_sync_all();                // no CTA leaves while its peer can still store into / arrive on its shared memory
   if (warp == 7) {
     tcgen05_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");

@@ -100,8 +100,10 @@ static int clip_setup(dsg_engine* e) {
   TRY(make_tmap(&t->tm_c128, t->wK256, rows256, D, 128));
   TRY(make_tmap(&t->tm_c64, t->wK256, rows256, D, 64));
   TRY(make_tmap(&t->tm_cw2, t->wK1024, (uint64_t)NL * D, F, 128));
-  CUDA_TRY(cudaFuncSetAttribute(clip::clip_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-  CUDA_TRY(cudaFuncSetAttribute(clip::clip_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  CUDA_TRY(cudaFuncSetAttribute(clip::clip_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  CUDA_TRY(cudaFuncSetAttribute(clip::clip_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  CUDA_TRY(cudaFuncSetAttribute(clip::clip_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  CUDA_TRY(cudaFuncSetAttribute(clip::clip_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   t->clip_ok = true;
   return DSG_OK;
 }
@@ -115,7 +117,12 @@ static int clip_run(dsg_engine* e, int B, float* xd, int k0, int n_run, int firs
   p.B = B; p.n_run = n_run; p.sampler = e->sampler;
   p.prof = getenv("DSG_CLIP_PROF") ? t->prof : nullptr;
   p.dbg = e->dbg; p.dbg_slot = (long long)e->d.max_batch * e->S * e->d.latent_dim; p.debug = e->debug ? 1 : 0;
-  const int grid = B < e->num_sms ? B : e->num_sms;
+  // Fewer clips than half the SMs: a CTA PAIR (cluster of 2) per clip, each streaming half of the attention / FFN weights
+  // (dsg_clip_kernel.cuh, CL = 2).  DSG_CLIP_PAIR=0 / 1 disables it.
+  const char* pair_env = getenv("DSG_CLIP_PAIR");
+  const bool pair = 2 * B <= e->num_sms && !(pair_env && !strcmp(pair_env, "0"));
+  const int slots = B < e->num_sms ? B : e->num_sms;          // clips in flight
+  const int grid = pair ? 2 * B : slots;
   clip::pack_xa_kernel<<<dim3(clip::JPAD / 64, B), 256, 0, st>>>(xd, t->xa);       // x_T as the first step's A k-blocks
   e->launches++;
   // The per-CTA noise scratch (grid x 401 KB) is written by the noise warp and bulk-copied back ~100-300 us later, every step: an
@@ -123,7 +130,7 @@ static int clip_run(dsg_engine* e, int B, float* xd, int k0, int n_run, int firs
   static const bool l2_persist = !(getenv("DSG_L2_PERSIST") && !strcmp(getenv("DSG_L2_PERSIST"), "0"));
   bool window_set = false;
   if (l2_persist) {
-    const size_t zbytes = (size_t)grid * clip::J * clip::T * sizeof(float);
+    const size_t zbytes = (size_t)slots * clip::J * clip::T * sizeof(float);
     if (!t->l2_limit_set) {
       cudaDeviceProp prop;
       if (cudaGetDeviceProperties(&prop, e->d.device) == cudaSuccess && prop.persistingL2CacheMaxSize > 0) {
@@ -146,8 +153,19 @@ static int clip_run(dsg_engine* e, int B, float* xd, int k0, int n_run, int firs
       cudaGetLastError();
     }
   }
-  if (p.prof) clip::clip_kernel<true><<<grid, 512, clip::SMEM_BYTES, st>>>(t->tm_cin, t->tm_c128, t->tm_c64, t->tm_cw2, p);
-  else clip::clip_kernel<false><<<grid, 512, clip::SMEM_BYTES, st>>>(t->tm_cin, t->tm_c128, t->tm_c64, t->tm_cw2, p);
+  if (pair) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(512); cfg.dynamicSmemBytes = clip::SMEM_BYTES; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    // (a launch error stays in cudaGetLastError, checked below once the access-policy window is off the stream again)
+    if (p.prof) cudaLaunchKernelEx(&cfg, clip::clip_kernel<true, 2>, t->tm_cin, t->tm_c128, t->tm_c64, t->tm_cw2, p);
+    else cudaLaunchKernelEx(&cfg, clip::clip_kernel<false, 2>, t->tm_cin, t->tm_c128, t->tm_c64, t->tm_cw2, p);
+  } else if (p.prof) clip::clip_kernel<true, 1><<<grid, 512, clip::SMEM_BYTES, st>>>(t->tm_cin, t->tm_c128, t->tm_c64, t->tm_cw2, p);
+  else clip::clip_kernel<false, 1><<<grid, 512, clip::SMEM_BYTES, st>>>(t->tm_cin, t->tm_c128, t->tm_c64, t->tm_cw2, p);
   e->launches++;
   if (window_set) {                        // the window applies to launches made while it is set: take it off the caller's stream again
     cudaStreamAttrValue av;

@@ -164,8 +164,10 @@ def test_clip_kernel_matches_multikernel_path(sd):
     assert mx < 0.05 and rms < 0.008
 
 
-def test_clip_kernel_many_clips_per_cta(sd):
-    """More clips than SMs: CTAs loop over several clips; results must equal a run where every clip has its own CTA."""
+def test_clip_kernel_many_clips_per_cta(sd, monkeypatch):
+    """More clips than SMs: CTAs loop over several clips; results must equal a run where every clip has its own CTA.
+    (Both runs in the one-CTA-per-clip mode: the CTA-pair mode small batches select sums linear2 in another order.)"""
+    monkeypatch.setenv("DSG_CLIP_PAIR", "0")
     d = create_gaussian_diffusion([3])
     B = 150
     y = synthetic_conditioning(G, B, segment=0)
@@ -178,12 +180,58 @@ def test_clip_kernel_many_clips_per_cta(sd):
     assert _err(part, full[147:150])[0] < 1e-5
 
 
+def test_clip_pair_mode_matches_single_cta_mode(sd, monkeypatch):
+    """Batches of at most SMs / 2 clips run a CLUSTER of two CTAs per clip (dsg_clip_kernel.cuh, CL = 2: heads, FFN chunks and
+    pose-head tiles split over the pair, exchanges through distributed shared memory).  Same arithmetic except for the order of
+    the linear2 sum and its bf16 hand-over: against the one-CTA mode and the fp32 oracle within the loop tolerance, per-layer
+    taps included; bitwise reproducible; independent of the batch composition; the largest pair batch (74 clips) included."""
+    d = create_gaussian_diffusion([6])
+    B = 3
+    y = synthetic_conditioning(G, B, segment=0)
+    shp = (B, G.njoints, 1, G.n_poses)
+    res = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("DSG_CLIP_PAIR", mode)
+        m = _model(sd, max_batch=B)
+        eng = m.get_engine(B)
+        eng.debug_enable()
+        out = d.p_sample_loop(m, shp, clip_denoised=False, model_kwargs={'y': dict(y, noise_seed=SEED, segment=0)})
+        res[mode] = (out.cpu(), {k: eng.debug_read(k, B) for k in ("xs0", "xs1", "xs4", "xs8")})
+    for k in ("xs0", "xs1", "xs4", "xs8"):
+        mx, rms = _err(res["1"][1][k], res["0"][1][k])
+        print(f"pair vs single tap {k}: max {mx:.3g} rms {rms:.3g}")
+        assert mx < 0.08 and rms < 0.01, k
+    want, _ = O.p_sample_loop(sd, G, O.Schedule(1000, [6]), y, B, seed=SEED, segment=0)
+    for mode in ("0", "1"):
+        mx, rms = _err(res[mode][0], want)
+        print(f"{'pair' if mode == '1' else 'single'} vs oracle, 6 steps: max {mx:.3g} rms {rms:.3g}")
+        assert mx < 0.05 and rms < 0.008
+    # 40 steps, 74 clips (148 CTAs): reproducible, finite, equal to the same clips run as a batch of 2, close to the one-CTA mode
+    d = create_gaussian_diffusion([40])
+    B = 74
+    y = synthetic_conditioning(G, B, segment=1)
+    m = _model(sd, max_batch=B)
+    kw = lambda yy, ids: {'y': dict(yy, noise_seed=SEED, segment=1, clip_ids=ids)}
+    monkeypatch.setenv("DSG_CLIP_PAIR", "1")
+    a = d.p_sample_loop(m, (B, G.njoints, 1, G.n_poses), clip_denoised=False, model_kwargs=kw(y, list(range(B)))).clone()
+    b = d.p_sample_loop(m, (B, G.njoints, 1, G.n_poses), clip_denoised=False, model_kwargs=kw(y, list(range(B)))).clone()
+    assert bool(torch.isfinite(a).all()) and torch.equal(a, b)
+    ys = {k: (v[72:74] if isinstance(v, torch.Tensor) and v.shape[0] == B else v) for k, v in y.items()}
+    part = d.p_sample_loop(m, (2, G.njoints, 1, G.n_poses), clip_denoised=False, model_kwargs=kw(ys, [72, 73]))
+    assert torch.equal(part, a[72:74])
+    monkeypatch.setenv("DSG_CLIP_PAIR", "0")
+    single = d.p_sample_loop(m, (B, G.njoints, 1, G.n_poses), clip_denoised=False, model_kwargs=kw(y, list(range(B))))
+    mx, rms = _err(a, single)
+    print(f"pair vs single, 74 clips x 40 steps: max {mx:.3g} rms {rms:.3g}")
+    assert mx < 0.05 and rms < 0.008
+
+
 def test_clip_kernel_is_bitwise_reproducible(sd):
     """Race detector: the persistent kernel synchronises 16 warps through ~40 mbarriers, named barriers and proxy fences
     with no host involvement; any missing edge shows up as run-to-run differences.  Same inputs -> identical bits, for
     one clip per CTA, several clips per CTA, and a single clip (different relative timing of the roles)."""
     d = create_gaussian_diffusion([40])
-    for B in (148, 150, 1):
+    for B in (148, 150, 1):                 # (B = 1 runs the CTA-pair mode)
         y = synthetic_conditioning(G, B, segment=1)
         m = _model(sd, max_batch=B)
         outs = []
