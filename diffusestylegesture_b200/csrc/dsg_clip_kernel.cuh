@@ -301,12 +301,12 @@ static __global__ void __launch_bounds__(256) pack_xa_kernel(const float* __rest
 // whole residual stream (XS) but streams and multiplies only its share of the weights:
 //   in_proj + global attention: 2 of the 4 heads per CTA; the head outputs are written into BOTH CTAs' BUF (distributed shared
 //       memory stores + a remote arrival on the peer's B_BUFR), so each CTA runs the full out_proj + LayerNorm 1 on its own;
-//   FFN: 4 of the 8 hidden chunks per CTA = a K-split of linear2; the fp32 partial sums are exchanged by ROW OWNERSHIP (rank 0
+//   FFN: 4 of the 8 hidden chunks per CTA = a K-split of linear2; the partial sums are exchanged (as bf16) by ROW OWNERSHIP (rank 0
 //       owns TMEM lane quarters 0 and 2, rank 1 quarter 1): a non-owner warp writes its 64 columns into the owner's receive
 //       buffer (BUF: the linear2 ring keeps to the attention staging area in this mode), the owner adds them, runs LayerNorm 2
 //       and writes the bf16 rows into both CTAs' XS (remote arrivals on B_XSR);
 //   pose head: tiles 0..4 / 5..8; x_t and its bf16 image meet in global memory (B_XAR counts both CTAs' worker warps).
-//   The input GEMM, the local attention, out_proj and LayerNorm 1 are computed by both CTAs (16 % of the weight bytes).
+//   The input GEMM, the local attention, out_proj and LayerNorm 1 are computed by both CTAs (12 % of the weight bytes).
 // Write-after-read across the pair is covered by data dependencies except for BUF, for which the peer sends a token (B_PFREE)
 // when its reads are over: once per step after the local attention (Z staging), once per layer after out_proj.
 template <bool PROF, int CL>
