@@ -1,5 +1,7 @@
 #!/bin/bash
-# compute-sanitizer racecheck + synccheck of the persistent clip kernel (3 DDPM steps, 2 clips, bf16).  Run under gpurun.
+# compute-sanitizer racecheck + synccheck + memcheck of the persistent clip kernel (3 DDPM steps, 2 clips, bf16).  Run under gpurun.
+#   PAIR=0 (default) : the one-CTA-per-clip kernel (DSG_CLIP_PAIR=0)          -> gpurun_out/r02_sanitizer.log
+#   PAIR=1 TOOLS="synccheck memcheck" : the CTA-pair kernel (cluster of two)  -> gpurun_out/r02_sanitizer_pair.log
 # The kernel synchronises 16 warps through 45 mbarriers, two named barriers and async-proxy fences; racecheck tracks
 # shared-memory hazards between generic-proxy accesses (st.shared / ld.shared of the epilogues).
 set -e
@@ -22,8 +24,13 @@ out = d.p_sample_loop(m, (B, g.njoints, 1, g.n_poses), clip_denoised=False, mode
 torch.cuda.synchronize()
 print("finite", bool(torch.isfinite(out).all()), "absmax", float(out.abs().max()))
 PY
-for tool in synccheck racecheck memcheck; do
-  echo "=== compute-sanitizer --tool $tool ===" >> gpurun_out/r02_sanitizer.log
-  timeout 900 compute-sanitizer --tool $tool --kernel-regex kns=clip_kernel --print-limit 20 python /tmp/clip_small.py >> gpurun_out/r02_sanitizer.log 2>&1 || echo "(exit $?)" >> gpurun_out/r02_sanitizer.log
+PAIR=${PAIR:-0}
+TOOLS=${TOOLS:-"synccheck racecheck memcheck"}
+LOG=gpurun_out/r02_sanitizer$([ "$PAIR" = 1 ] && echo _pair).log
+export DSG_CLIP_PAIR=$PAIR
+: > $LOG
+for tool in $TOOLS; do
+  echo "=== compute-sanitizer --tool $tool (DSG_CLIP_PAIR=$PAIR) ===" >> $LOG
+  timeout 600 compute-sanitizer --tool $tool --kernel-regex kns=clip_kernel --print-limit 20 python /tmp/clip_small.py >> $LOG 2>&1 || echo "(exit $?)" >> $LOG
 done
-grep -E "===|ERROR SUMMARY|RACECHECK SUMMARY|finite|exit" gpurun_out/r02_sanitizer.log
+grep -E "===|ERROR SUMMARY|RACECHECK SUMMARY|finite|exit" $LOG
