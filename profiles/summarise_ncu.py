@@ -31,6 +31,7 @@ def main():
     ap.add_argument("--note", default="")
     ap.add_argument("--kernel", default="clip_kernel")
     ap.add_argument("--all", action="store_true", help="keep every metric, not just the short list")
+    ap.add_argument("--no-traffic-json", action="store_true", help="do not rewrite clip_kernel_traffic.json (captures of other launch shapes)")
     a = ap.parse_args()
     raw = subprocess.run(["ncu", "-i", a.rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
@@ -55,7 +56,7 @@ def main():
         u, v = vals[k]
         x = float(v.replace(",", ""))
         return x * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "Tbyte": 1e12}.get(u, 1.0)
-    if "dram__bytes_read.sum" in vals:
+    if "dram__bytes_read.sum" in vals and not a.no_traffic_json:
         per = (num("dram__bytes_read.sum") + num("dram__bytes_write.sum")) / (a.clips * a.steps)
         out = {"dram_bytes_per_clip_step": per, "source": os.path.basename(a.out_csv) + f" ({a.clips} clips x {a.steps} steps)",
                "clips": a.clips, "steps": a.steps}
