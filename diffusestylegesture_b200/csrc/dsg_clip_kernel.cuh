@@ -123,8 +123,12 @@ DSG_DEVINL uint32_t map_to_cta(uint32_t saddr, uint32_t rank) {
 DSG_DEVINL void st_remote16(uint32_t raddr, const uint4 v) {
   asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(raddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
-DSG_DEVINL void st_remote16f(uint32_t raddr, const float* v) {
-  asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(raddr), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
+DSG_DEVINL void bulk_copy_to_peer(uint32_t rdst, const void* src, uint32_t bytes, uint32_t rbar) {
+  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(rdst), "r"(smem_u32(src)), "r"(bytes), "r"(rbar) : "memory");
+}
+DSG_DEVINL void mbar_arrive_expect_tx_remote(uint32_t rbar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.release.cluster.shared::cluster.b64 _, [%0], %1;" ::"r"(rbar), "r"(bytes) : "memory");
 }
 DSG_DEVINL void mbar_arrive_remote(uint32_t rbar) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(rbar) : "memory");
@@ -142,17 +146,6 @@ DSG_DEVINL void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {      // acqu
       "bra WAITC_%=;\n\t"
       "DONEC_%=:\n\t"
       "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-// Diagnostic (off): every lane that stored into the peer's shared memory fences at cluster scope before the warp's one arrival.
-// Not needed: __syncwarp orders the lanes' stores before lane 0's release.cluster arrival (cumulativity), and where the data is
-// read through the async proxy each lane has already run fence.proxy.async (a MEMBAR.ALL.GPU).  Measured: 2 us per exchange.
-#ifndef DSG_PAIR_FENCE
-#define DSG_PAIR_FENCE 0
-#endif
-DSG_DEVINL void pair_fence() {
-#if DSG_PAIR_FENCE
-  asm volatile("fence.acq_rel.cluster;" ::: "memory");
-#endif
 }
 DSG_DEVINL void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -299,12 +292,12 @@ static __global__ void __launch_bounds__(256) pack_xa_kernel(const float* __rest
 // ---------------------------------------------------------------------------------------------------
 // CL = 1: one CTA per clip.  CL = 2 (batches smaller than half the SMs): a CLUSTER of two CTAs per clip.  Each CTA keeps the
 // whole residual stream (XS) but streams and multiplies only its share of the weights:
-//   in_proj + global attention: 2 of the 4 heads per CTA; the head outputs are written into BOTH CTAs' BUF (distributed shared
-//       memory stores + a remote arrival on the peer's B_BUFR), so each CTA runs the full out_proj + LayerNorm 1 on its own;
+//   in_proj + global attention: 2 of the 4 heads per CTA; the head outputs go into BOTH CTAs' BUF (a bulk copy of the two
+//       k-tiles into the peer's shared memory, counted on the peer's B_BUFR), so each CTA runs the full out_proj + LayerNorm 1;
 //   FFN: 4 of the 8 hidden chunks per CTA = a K-split of linear2; the partial sums are exchanged (as bf16) by ROW OWNERSHIP (rank 0
 //       owns TMEM lane quarters 0 and 2, rank 1 quarter 1): a non-owner warp writes its 64 columns into the owner's receive
 //       buffer (BUF: the linear2 ring keeps to the attention staging area in this mode), the owner adds them, runs LayerNorm 2
-//       and writes the bf16 rows into both CTAs' XS (remote arrivals on B_XSR);
+//       and the bf16 rows go into both CTAs' XS (one 16 KB bulk copy per owned quarter, counted on the peer's B_XSR);
 //   pose head: tiles 0..4 / 5..8; x_t and its bf16 image meet in global memory (B_XAR counts both CTAs' worker warps).
 //   The input GEMM, the local attention, out_proj and LayerNorm 1 are computed by both CTAs (12 % of the weight bytes).
 // Write-after-read across the pair is covered by data dependencies except for BUF, for which the peer sends a token (B_PFREE)
@@ -788,7 +781,6 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
 #pragma unroll
           for (int i = 0; i < 8; ++i) st_remote16(peer_smem + rx_off + i * (RXROWS * 16), pack8(v + 8 * i));
         }
-        pair_fence();
         __syncwarp();
         if (lane == 0) mbar_arrive_remote(peer_bars + B_RX * 8);
         lap(PF_W_LN);
@@ -840,12 +832,18 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
         const uint32_t off = (uint32_t)OFF_XS + xs_off(r, col0 + i * 8);
         const uint4 u = pack8(v + i * 8);
         *reinterpret_cast<uint4*>(smem + off) = u;
-        st_remote16(peer_smem + off, u);
       }
-      fence_async_all();
-      pair_fence();
+      // the quarter's 32 rows are one contiguous 16 KB block of XS (row-group-major): one bulk copy per owned quarter into the peer's
+      fence_async_smem();
+      quarter_sync(q4);
+      if (sub == 0 && lane == 0)
+        bulk_copy_to_peer(peer_smem + OFF_XS + q4 * 4 * 4096, smem + OFF_XS + q4 * 4 * 4096, 4 * 4096, peer_bars + B_XSR * 8);
       __syncwarp();
-      if (lane == 0) { mbar_arrive(&bars[B_XSR]); mbar_arrive_remote(peer_bars + B_XSR * 8); }
+      if (lane == 0) {
+        mbar_arrive(&bars[B_XSR]);
+        if (sub == 0) mbar_arrive_expect_tx_remote(peer_bars + B_XSR * 8, 4 * 4096);      // announces the copy's bytes
+        else mbar_arrive_remote(peer_bars + B_XSR * 8);
+      }
       lap(PF_W_LN);
     };
     auto debug_dump = [&](int slot, int clip) {
@@ -1127,17 +1125,32 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
               const uint4 u0 = pack8(o16), u1 = pack8(o16 + 8);
               *reinterpret_cast<uint4*>(smem + o_off) = u0;
               *reinterpret_cast<uint4*>(smem + o_off8) = u1;
-              if constexpr (CL > 1) { st_remote16(peer_smem + o_off, u0); st_remote16(peer_smem + o_off8, u1); }   // out_proj runs on both CTAs
             }
             tcgen05_fence_before();
-            // (CTA pair: the tensor core reads BUF only after the second head, whose fence covers this thread's stores of both)
-            if constexpr (CL > 1) { if (hb == 1) { fence_async_all(); pair_fence(); } } else fence_async_smem();
+            fence_async_smem();
+            if constexpr (CL > 1) {
+              // out_proj runs on both CTAs: once both heads of this CTA are in BUF (k-tiles h - 1, h: 12 KB of token rows each) and
+              // every worker's stores are fenced for the async proxy, ONE thread copies them into the peer's BUF.  (Per-thread
+              // st.shared::cluster of the same data: 16 B per 32 B sector on the SM-to-SM path and a GPU-scope membar per warp,
+              // 11 us per step slower.)
+              if (hb == 1) {
+                workers_sync();
+                if (wt == 0) {
+                  const uint32_t rb = peer_bars + (B_BUFR + (h >> 1)) * 8;
+                  bulk_copy_to_peer(peer_smem + OFF_BUF + (h - 1) * KT, smem + OFF_BUF + (h - 1) * KT, XA_ROWS_BYTES, rb);
+                  bulk_copy_to_peer(peer_smem + OFF_BUF + h * KT, smem + OFF_BUF + h * KT, XA_ROWS_BYTES, rb);
+                }
+              }
+            }
             __syncwarp();
             if (lane == 0) {
               mbar_arrive(&bars[B_ACCF + 2 * hb]); mbar_arrive(&bars[B_ACCF + 2 * hb + 1]);      // the head's TMEM half is free
               if (hb == 1) {                                                                       // both heads of this BUF half are written
                 mbar_arrive(&bars[B_BUFR + (h >> 1)]);
-                if constexpr (CL > 1) mbar_arrive_remote(peer_bars + (B_BUFR + (h >> 1)) * 8);
+                if constexpr (CL > 1) {                                                            // (warp 0 announces the copies' bytes)
+                  if (wl == 0) mbar_arrive_expect_tx_remote(peer_bars + (B_BUFR + (h >> 1)) * 8, 2 * XA_ROWS_BYTES);
+                  else mbar_arrive_remote(peer_bars + (B_BUFR + (h >> 1)) * 8);
+                }
               }
             }
             lap(PF_W_ATT_MERGE);
@@ -1235,7 +1248,6 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
           }
         }
         fence_async_all();                               // x and its k-block image are read back by bulk copies (async proxy)
-        if constexpr (CL > 1) pair_fence();
         __syncwarp();
         if (lane == 0) {
           if constexpr (CL > 1) { mbar_arrive_release_cluster(&bars[B_XAR]); mbar_arrive_remote(peer_bars + B_XAR * 8); }
