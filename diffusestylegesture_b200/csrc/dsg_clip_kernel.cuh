@@ -299,7 +299,9 @@ static __global__ void __launch_bounds__(256) pack_xa_kernel(const float* __rest
 //       buffer (BUF: the linear2 ring keeps to the attention staging area in this mode), the owner adds them, runs LayerNorm 2
 //       and the bf16 rows go into both CTAs' XS (one 16 KB bulk copy per owned quarter, counted on the peer's B_XSR);
 //   pose head: tiles 0..4 / 5..8; x_t and its bf16 image meet in global memory (B_XAR counts both CTAs' worker warps).
-//   The input GEMM, the local attention, out_proj and LayerNorm 1 are computed by both CTAs (12 % of the weight bytes).
+//   input GEMM + local attention: the 128 latent columns = 4 local heads of the rank; the halves of XS are exchanged as 12 bulk
+//       copies of 2 KB (one per 8-row group), announced on the RECEIVER's B_XSR by one of its own arrivals (arrive.expect_tx);
+//   out_proj and LayerNorm 1 are computed by both CTAs (8 % of the weight bytes).
 // Write-after-read across the pair is covered by data dependencies except for BUF, for which the peer sends a token (B_PFREE)
 // when its reads are over: once per step after the local attention (Z staging), once per layer after out_proj.
 template <bool PROF, int CL>
@@ -407,7 +409,8 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
               bulk_load(smem + OFF_BUF + sl * KT, xa + (long long)kb * KT, XA_ROWS_BYTES, &bars[B_AFULL + sl]);
             }
             __syncwarp();
-            for (int nh = 0; nh < 2; ++nh) load(&tm_in, nh * 128, kb * 64, WSTAGE);
+            // (CTA pair: each CTA computes the 128 latent columns = 4 local heads of its rank)
+            for (int nh = (CL > 1 ? rank : 0); nh < (CL > 1 ? rank + 1 : 2); ++nh) load(&tm_in, nh * 128, kb * 64, WSTAGE);
           }
           for (int l = 0; l < NL; ++l) {
             const int rb = l * R_LAYER;
@@ -516,7 +519,7 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
           for (int kb = 0; kb < JPAD / 64; ++kb) {
             owait(B_AFULL + (kb & 3));
             tcgen05_fence_after();
-            for (int nh = 0; nh < 2; ++nh) tile(buf_addr + (kb & 3) * KT, nh * 128, idesc128, kb > 0);
+            for (int nh = (CL > 1 ? rank : 0); nh < (CL > 1 ? rank + 1 : 2); ++nh) tile(buf_addr + (kb & 3) * KT, nh * 128, idesc128, kb > 0);
             if (elect_one()) { tcgen05_commit(&bars[B_AEMPTY + (kb & 3)]); }
           }
           if (elect_one()) { tcgen05_commit(&bars[B_ACCR + 0]); tcgen05_commit(&bars[B_ACCR + 1]); }
@@ -883,8 +886,9 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
           const bool ok = r >= 1 && r <= T;
           float v[32];
 #pragma unroll 1
-          for (int c2 = 0; c2 < 2; ++c2) {
-            const int col0 = sub * 64 + c2 * 32;       // == local head (sub*2 + c2) * 32
+          for (int c2 = 0; c2 < (CL > 1 ? 1 : 2); ++c2) {
+            // == local head (sub*2 + c2) * 32; CTA pair: the rank's 128 columns, 32 per column quarter
+            const int col0 = CL > 1 ? rank * 128 + sub * 32 : sub * 64 + c2 * 32;
             tmem_ld32(tlane + col0, v);
             if (!ok) continue;
             const float* cr = condc + (long long)f * D + col0;
@@ -910,8 +914,8 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
         workers_sync();
         lap(PF_W_IN_EPI);
         // ---------------- windowed causal local attention on mma.sync (q = k = v = Z), rotary (position = frame + 1) -> XS
-        for (int item = wl; item < 64; item += NW) {
-          const int w = item >> 3, lh = item & 7;
+        for (int item = wl; item < 64 / CL; item += NW) {
+          const int w = CL > 1 ? item >> 2 : item >> 3, lh = CL > 1 ? rank * 4 + (item & 3) : item & 7;
           const int q0 = WIN * w, k0 = (w == 0) ? 0 : WIN * (w - 1), nk = q0 + WIN - k0;
           float sc[4][4];
 #pragma unroll
@@ -987,13 +991,23 @@ clip_kernel(const __grid_constant__ CUtensorMap tm_in,     // Wxp   [256, 1152] 
             }
           }
         }
-        if (wt < D) {   // token row: tok = emb_1 + emb_t (rotary at position 0 is the identity)
-          const float tv = __ldg(P.emb1 + (long long)clip * D + wt) + __ldg(P.te + (long long)trow * D + wt);
-          *reinterpret_cast<__nv_bfloat16*>(XS + xs_off(0, wt)) = __float2bfloat16_rn(tv);
+        if (wt < D / CL) {   // token row: tok = emb_1 + emb_t (rotary at position 0 is the identity)
+          const int tc = CL > 1 ? rank * 128 + wt : wt;
+          const float tv = __ldg(P.emb1 + (long long)clip * D + tc) + __ldg(P.te + (long long)trow * D + tc);
+          *reinterpret_cast<__nv_bfloat16*>(XS + xs_off(0, tc)) = __float2bfloat16_rn(tv);
         }
         fence_async_smem();
         workers_sync();                                  // Z staging (BUF) is dead from here on
-        if (lane == 0) mbar_arrive(&bars[B_XSR]);
+        if constexpr (CL > 1) {
+          // this CTA's 128 columns (k-tiles 2 rank, 2 rank + 1: 2 KB per 8-row group of the row-group-major XS) go into the peer's XS
+          // as 12 bulk copies counted on the peer's B_XSR; the bytes coming the other way are announced on OUR barrier by warp 0
+          if (wl == 0 && lane < 12) {
+            const uint32_t off = (uint32_t)(OFF_XS + lane * 4096 + rank * 2048);
+            bulk_copy_to_peer(peer_smem + off, smem + off, 2048, peer_bars + B_XSR * 8);
+          }
+          __syncwarp();
+          if (lane == 0) { if (wl == 0) mbar_expect_tx(&bars[B_XSR], 12 * 2048); else mbar_arrive(&bars[B_XSR]); }
+        } else if (lane == 0) mbar_arrive(&bars[B_XSR]);
         if (CL > 1 && wt == 0) mbar_arrive_remote(peer_bars + B_PFREE * 8);      // ... and the peer may write head outputs into it
         lap(PF_W_LOCAL);
         debug_dump(0, clip);

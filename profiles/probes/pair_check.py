@@ -59,10 +59,8 @@ B = 2
 d = create_gaussian_diffusion([2])
 y = synthetic_conditioning(G, B, segment=0)
 taps = {}
-for mode in (() if a.no_taps else ("0", "1", "1b", "1d")):
+for mode in (() if a.no_taps else ("0", "1", "1b")):
     os.environ["DSG_CLIP_PAIR"] = mode[0]
-    if mode == "1d":
-        os.environ["DSG_PAIR_DELAY"] = "1"
     m = model(B)
     eng = m.get_engine(B)
     eng.debug_enable()
@@ -70,10 +68,9 @@ for mode in (() if a.no_taps else ("0", "1", "1b", "1d")):
                           model_kwargs={'y': dict(y, noise_seed=123456, segment=0, clip_ids=list(range(B)))}).clone()
     taps[mode] = {k: eng.debug_read(k, B).clone().reshape(B, 89, 256) for k in ["xs%d" % i for i in range(9)]}
     taps[mode]["out"] = out.cpu().reshape(B, G.njoints, G.n_poses).permute(0, 2, 1)
-os.environ.pop("DSG_PAIR_DELAY", None)
 rms = lambda t: float(t.pow(2).mean().sqrt())
 for k in ([] if a.no_taps else taps["0"]):
-    for other in ("1", "1d"):
+    for other in ("1",):
         e = (taps[other][k] - taps["0"][k])
         line = f"tap {k} pair{other[1:]} vs single: max {float(e.abs().max()):.3g} rms {rms(e):.3g}"
         if k != "out":
