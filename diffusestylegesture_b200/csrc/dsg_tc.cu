@@ -43,6 +43,7 @@ struct dsg_tc_state {
   CUtensorMap tm_cin, tm_c128, tm_c64, tm_cw2;
   bool l2_limit_set = false;
   size_t l2_window_max = 0;
+  int pair_clusters = -1;          // CTA pairs (clusters of 2) the device can keep resident at once; -1 = not asked yet
 };
 
 #include "dsg_tc_host.cuh"
@@ -117,10 +118,23 @@ static int clip_run(dsg_engine* e, int B, float* xd, int k0, int n_run, int firs
   p.B = B; p.n_run = n_run; p.sampler = e->sampler;
   p.prof = getenv("DSG_CLIP_PROF") ? t->prof : nullptr;
   p.dbg = e->dbg; p.dbg_slot = (long long)e->d.max_batch * e->S * e->d.latent_dim; p.debug = e->debug ? 1 : 0;
-  // Fewer clips than half the SMs: a CTA PAIR (cluster of 2) per clip, each streaming half of the attention / FFN weights
-  // (dsg_clip_kernel.cuh, CL = 2).  DSG_CLIP_PAIR=0 / 1 disables it.
+  // Fewer clips than half the SMs: a CTA PAIR (cluster of 2) per clip, each streaming half of the weights (dsg_clip_kernel.cuh,
+  // CL = 2) — as long as the device keeps that many clusters of this size resident at once (74 on a full B200; fewer, or none, on
+  // a partitioned one).  DSG_CLIP_PAIR=0 disables it.
+  if (t->pair_clusters < 0) {
+    cudaLaunchConfig_t occ;
+    memset(&occ, 0, sizeof occ);
+    occ.gridDim = dim3(2 * (e->num_sms / 2)); occ.blockDim = dim3(512); occ.dynamicSmemBytes = clip::SMEM_BYTES;
+    cudaLaunchAttribute oa[1];
+    oa[0].id = cudaLaunchAttributeClusterDimension;
+    oa[0].val.clusterDim.x = 2; oa[0].val.clusterDim.y = 1; oa[0].val.clusterDim.z = 1;
+    occ.attrs = oa; occ.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, clip::clip_kernel<false, 2>, &occ) != cudaSuccess) { n = 0; cudaGetLastError(); }
+    t->pair_clusters = n;
+  }
   const char* pair_env = getenv("DSG_CLIP_PAIR");
-  const bool pair = 2 * B <= e->num_sms && !(pair_env && !strcmp(pair_env, "0"));
+  const bool pair = B <= t->pair_clusters && 2 * B <= e->num_sms && !(pair_env && !strcmp(pair_env, "0"));
   const int slots = B < e->num_sms ? B : e->num_sms;          // clips in flight
   const int grid = pair ? 2 * B : slots;
   clip::pack_xa_kernel<<<dim3(clip::JPAD / 64, B), 256, 0, st>>>(xd, t->xa);       // x_T as the first step's A k-blocks
